@@ -1,0 +1,105 @@
+// device_math.cuh — special functions used by the Mr.LDA kernels (fp64).
+//
+// digamma / trigamma follow the lda-c style series that cloud9's Gamma class uses; the reference's
+// known-answer tests pin them (src/test/java/cc/mrlda/VariationalInferenceTest.java:27-62).  Call
+// sites replaced: DocumentMapper.java:209,256,258; TermReducer.java:173,195,213,233;
+// VariationalInference.java:434,438,449,597-603.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace mrlda {
+
+// Literal operation order (no FMA contraction) — used where the (x+6)-6 cancellation is visible in
+// the result: the beta finalize evaluates digamma(1e-12 + s) ~ -1e12 and must round like Java does.
+__device__ __forceinline__ double digamma_literal(double x) {
+  double x6 = __dadd_rn(x, 6.0);
+  double p = __ddiv_rn(1.0, __dmul_rn(x6, x6));
+  p = __dmul_rn(
+      __dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(0.004166666666667, p),
+                                                         -0.003968253986254), p),
+                                    0.008333333333333), p),
+                -0.083333333333333), p);
+  double r = __dadd_rn(p, log(x6));
+  r = __dadd_rn(r, -__ddiv_rn(0.5, x6));
+  r = __dadd_rn(r, -__ddiv_rn(1.0, __dadd_rn(x6, -1.0)));
+  r = __dadd_rn(r, -__ddiv_rn(1.0, __dadd_rn(x6, -2.0)));
+  r = __dadd_rn(r, -__ddiv_rn(1.0, __dadd_rn(x6, -3.0)));
+  r = __dadd_rn(r, -__ddiv_rn(1.0, __dadd_rn(x6, -4.0)));
+  r = __dadd_rn(r, -__ddiv_rn(1.0, __dadd_rn(x6, -5.0)));
+  r = __dadd_rn(r, -__ddiv_rn(1.0, __dadd_rn(x6, -6.0)));
+  return r;
+}
+
+__device__ __forceinline__ double trigamma_literal(double x) {
+  double x6 = __dadd_rn(x, 6.0);
+  double p = __ddiv_rn(1.0, __dmul_rn(x6, x6));
+  double q = __dadd_rn(__dmul_rn(0.075757575757576, p), -0.033333333333333);
+  q = __dadd_rn(__dmul_rn(q, p), 0.0238095238095238);
+  q = __dadd_rn(__dmul_rn(q, p), -0.033333333333333);
+  q = __dadd_rn(__dmul_rn(q, p), 0.166666666666667);
+  q = __dadd_rn(__dmul_rn(q, p), 1.0);
+  p = __dadd_rn(__ddiv_rn(q, x6), __dmul_rn(0.5, p));
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    x6 = __dadd_rn(x6, -1.0);
+    p = __dadd_rn(__ddiv_rn(1.0, __dmul_rn(x6, x6)), p);
+  }
+  return p;
+}
+
+// 1/x to ~1 ulp for normal positive x: MUFU.RCP64H seed + two Newton steps.
+__device__ __forceinline__ double rcp_fast(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// The same digamma series restructured for the E-step's inner fixed point
+// (DocumentMapper.java:208-211 evaluates it K times per sweep, 99 sweeps per document):
+//   psi(x) = P(1/x6^2) + log(x6) - 0.5/x6 - sum_{j=0..5} 1/(t+j),  x6 = x+6, t = x6-6
+// with the six reciprocals folded into one rational Q'(t)/Q(t), Q(t) = t(t+1)...(t+5), and a single
+// reciprocal 1/(x6*Q).  t keeps the reference's (x+6)-6 rounding.  Returns u = psi(x) - log(x6) and
+// x6, so that exp(psi(x)) = x6 * exp(u) needs no logarithm.  |difference to the literal form| is a
+// few ulp of the largest term (no cancellation: all Q/Q' coefficients are positive).
+__device__ __forceinline__ double digamma_minus_log(double x, double &x6_out) {
+  double x6 = x + 6.0;
+  double t = x6 - 6.0;
+  double q = fma(fma(fma(fma(fma(t, 1.0, 15.0), t, 85.0), t, 225.0), t, 274.0), t, 120.0) * t;
+  double dq = fma(fma(fma(fma(fma(6.0, t, 75.0), t, 340.0), t, 675.0), t, 548.0), t, 120.0);
+  double inv = rcp_fast(x6 * q);   // 1/(x6*Q)
+  double rx6 = q * inv;            // 1/x6
+  double ratio = dq * (x6 * inv);  // Q'/Q
+  double p = rx6 * rx6;
+  p = fma(fma(fma(0.004166666666667, p, -0.003968253986254), p, 0.008333333333333), p,
+          -0.083333333333333) * p;
+  x6_out = x6;
+  return p - 0.5 * rx6 - ratio;
+}
+
+// psi(x) by the restructured series.
+__device__ __forceinline__ double digamma_fast(double x) {
+  double x6;
+  double u = digamma_minus_log(x, x6);
+  return u + log(x6);
+}
+
+// exp(psi(x)): the weight theta_k of the linear-space E-step.  Underflows to 0 for x << 1.
+__device__ __forceinline__ double exp_digamma(double x) {
+  double x6;
+  double u = digamma_minus_log(x, x6);
+  return x6 * exp(u);
+}
+
+// LogMath.add without a drop threshold (see oracle/mrlda_oracle.c header for the pinning status).
+__device__ __forceinline__ double logadd(double a, double b) {
+  double hi = fmax(a, b), lo = fmin(a, b);
+  if (hi == -INFINITY) return hi;
+  return hi + log1p(exp(lo - hi));
+}
+
+}  // namespace mrlda

@@ -1,0 +1,1139 @@
+// mrlda_capi.cu — context, model kernels (K2 beta finalize, K3 alpha update) and the C ABI of
+// libmrlda_b200.so declared in include/mrlda_b200.h.
+//
+// Reference code replaced here:
+//   TermCombiner.java:19-35, TermReducer.java:134-238   -> finalize_* kernels (K2)
+//   DocumentMapper.importBeta (DocumentMapper.java:475-536) -> import_beta_kernel
+//   DocumentMapper.retrieveBeta (:446-463)               -> init_beta_kernel (seeded, not Math.random)
+//   VariationalInference.updateVectorAlpha / updateScalarAlpha (VariationalInference.java:409-511,
+//   573-625, wrapper :295-311)                           -> alpha_*_kernel (K3)
+//   Hadoop shuffle + Counters (VariationalInference.java:242-243,260-268) -> one NCCL all-reduce
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/mrlda_b200.h"
+#include "estep_kernel.cuh"
+
+using namespace mrlda;
+
+// ------------------------------------------------------------------------------------------------
+// small device kernels
+// ------------------------------------------------------------------------------------------------
+
+// likelihoodAlpha = lngamma(sum alpha) - sum lngamma(alpha_k)  (DocumentMapper.java:121-126)
+__global__ void prep_kernel(const double *alpha, int K, double *lik_alpha) {
+  __shared__ double sa[32], sl[32];
+  double a = 0.0, l = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    a += alpha[k];
+    l += lgamma(alpha[k]);
+  }
+  a = warp_sum(a);
+  l = warp_sum(l);
+  if ((threadIdx.x & 31) == 0) {
+    sa[threadIdx.x >> 5] = a;
+    sl[threadIdx.x >> 5] = l;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ta = 0.0, tl = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
+      ta += sa[w];
+      tl += sl[w];
+    }
+    *lik_alpha = lgamma(ta) - tl;
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ double u01(uint64_t h) {  // (0,1)
+  return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+// retrieveBeta's initialisation log(2*U1/V + U2) (DocumentMapper.java:456) for rows with
+// only_absent ? present[v]==0 : all.
+__global__ void init_beta_kernel(double *logbeta, const uint8_t *present, int only_absent, int V,
+                                 int K, uint64_t seed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)V * K;
+  if (i >= n) return;
+  int v = (int)(i / K);
+  if (only_absent && present[v]) return;
+  uint64_t h1 = splitmix64(seed ^ splitmix64(2 * (uint64_t)i));
+  uint64_t h2 = splitmix64(seed ^ splitmix64(2 * (uint64_t)i + 1));
+  logbeta[i] = log(2.0 * u01(h1) / (double)V + u01(h2));
+}
+
+// importBeta: logbeta = value - (double)normaliserFloat for present rows (DocumentMapper.java:511)
+__global__ void import_beta_kernel(double *logbeta, const double *dl, const float *nrm,
+                                   const uint8_t *present, int V, int K) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t n = (int64_t)V * K;
+  if (i >= n) return;
+  int v = (int)(i / K), k = (int)(i - (int64_t)v * K);
+  if (present[v]) logbeta[i] = dl[i] - (double)nrm[k];
+}
+
+// m_v = max_k logbeta_vk; E_vk = exp(logbeta_vk - m_v), zero in the KS-K padding.  One warp per term.
+__global__ void expand_rows_kernel(const double *logbeta, double *E, double *rowmax, int V, int K,
+                                   int KS) {
+  int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= V) return;
+  const double *lb = logbeta + (size_t)warp * K;
+  double mx = -INFINITY;
+  for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k]);
+  mx = warp_max(mx);
+  double *e = E + (size_t)warp * KS;
+  for (int k = lane; k < KS; k += 32) e[k] = k < K ? exp(lb[k] - mx) : 0.0;
+  if (lane == 0) rowmax[warp] = mx;
+}
+
+// K2a: per-slab partial column sums of lambda = eta + stats over the terms seen in the corpus
+// (the logNormalizeFactor fold of TermReducer.java:189,212, in linear space), and present[v].
+// A term was emitted by some mapper iff sum_k stats[v][k] = n_v > 0.
+__global__ void finalize_colsum_kernel(const double *stats, int V, int K, double eta, int slab,
+                                       double *partial, uint8_t *present) {
+  extern __shared__ double rs[];  // slab row sums
+  int v0 = blockIdx.x * slab, v1 = min(V, v0 + slab);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int v = v0 + warp; v < v1; v += nw) {
+    const double *row = stats + (size_t)v * K;
+    double s = 0.0;
+    for (int k = lane; k < K; k += 32) s += row[k];
+    s = warp_sum(s);
+    if (lane == 0) {
+      rs[v - v0] = s;
+      present[v] = s > 0.0 ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    double acc = 0.0;
+    for (int v = v0; v < v1; v++)
+      if (rs[v - v0] > 0.0) acc += eta + stats[(size_t)v * K + k];
+    partial[(size_t)blockIdx.x * K + k] = acc;
+  }
+}
+
+// K2b: normaliser_k = (float) digamma(sum_v lambda_kv)  (TermReducer.java:173,233); fixed order.
+__global__ void finalize_norm_kernel(const double *partial, int nslabs, int K, float *nrm,
+                                     double *colsum) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  double s = 0.0;
+  for (int b = 0; b < nslabs; b++) s += partial[(size_t)b * K + k];
+  colsum[k] = s;
+  nrm[k] = s > 0.0 ? (float)digamma_literal(s) : 0.0f;
+}
+
+// K2c: per term row: digamma(lambda) (the beta file value, TermReducer.java:195,213), the
+// importBeta subtraction (DocumentMapper.java:511), row max and E.  One warp per term.
+__global__ void finalize_rows_kernel(const double *stats, const uint8_t *present, const float *nrm,
+                                     double eta, int V, int K, int KS, double *dl, double *logbeta,
+                                     double *E, double *rowmax) {
+  int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (warp >= V) return;
+  if (!present[warp]) return;  // no row in the beta file; keeps its previous logbeta / E
+  const double *row = stats + (size_t)warp * K;
+  double *dlr = dl + (size_t)warp * K, *lbr = logbeta + (size_t)warp * K;
+  double mx = -INFINITY;
+  for (int k = lane; k < K; k += 32) {
+    double lam = eta + row[k];
+    double v = digamma_literal(lam);
+    dlr[k] = v;
+    double lb = v - (double)nrm[k];
+    lbr[k] = lb;
+    mx = fmax(mx, lb);
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  double *e = E + (size_t)warp * KS;
+  for (int k = lane; k < KS; k += 32) e[k] = k < K ? exp(lbr[k] - mx) : 0.0;
+  if (lane == 0) rowmax[warp] = mx;
+}
+
+// K3 vector: VariationalInference.updateVectorAlpha (VariationalInference.java:409-511) with the
+// Java aliasing semantics: the first Newton pass writes a fresh vector, later passes update in place,
+// a singular step (alpha_i <= step) at index i leaves entries [0,i) updated once the arrays alias.
+// Single CTA; thread i owns topic i (+ blockDim strides).  io: alpha in/out.
+__global__ void alpha_vector_kernel(double *alpha, const double *ss, int K, int n_docs,
+                                    double *work /* 3K: grad, hess, fresh */) {
+  __shared__ double red[2][32];
+  __shared__ int sh_first, sh_flag;
+  double *grad = work, *hess = work + K, *fresh = work + 2 * K;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, NW = T >> 5;
+  const double D = (double)n_docs;
+  auto block_sum2 = [&](double a, double b, double &oa, double &ob) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) {
+      red[0][warp] = a;
+      red[1][warp] = b;
+    }
+    __syncthreads();
+    double ta = 0.0, tb = 0.0;
+    for (int w = 0; w < NW; w++) {
+      ta += red[0][w];
+      tb += red[1][w];
+    }
+    oa = ta;
+    ob = tb;
+  };
+  double *cur = alpha;   // "alphaVector"
+  bool aliased = false;  // alphaVectorUpdate == alphaVector ?
+  int decay = 0, iter = 0;
+  double alpha_sum, dummy;
+  {
+    double a = 0.0;
+    for (int i = tid; i < K; i += T) a += cur[i];
+    block_sum2(a, 0.0, alpha_sum, dummy);
+  }
+  bool keep_going = true;
+  while (keep_going) {
+    double g_h = 0.0, one_h = 0.0;
+    int bad = 0;
+    const double dsum = digamma_literal(alpha_sum);
+    for (int i = tid; i < K; i += T) {
+      double g = D * (dsum - digamma_literal(cur[i])) + ss[i];
+      double h = -D * trigamma_literal(cur[i]);
+      grad[i] = g;
+      hess[i] = h;
+      if (isinf(g)) bad = 1;
+      g_h += g / h;
+      one_h += 1.0 / h;
+    }
+    if (tid == 0) sh_flag = 0;
+    double sum_g_h, sum_1_h;
+    block_sum2(g_h, one_h, sum_g_h, sum_1_h);
+    if (bad) atomicOr(&sh_flag, 1);
+    __syncthreads();
+    if (sh_flag) break;  // ArithmeticException path (VariationalInference.java:440-443,505-508)
+    const double z = D * trigamma_literal(alpha_sum);
+    const double c = sum_g_h / (1.0 / z + sum_1_h);
+
+    double *upd = aliased ? cur : fresh;
+    for (;;) {
+      const double scale = pow((double)0.8f, (double)decay);
+      if (tid == 0) sh_first = K;
+      __syncthreads();
+      for (int i = tid; i < K; i += T) {
+        double step = scale * (grad[i] - c) / hess[i];
+        if (cur[i] <= step) atomicMin(&sh_first, i);
+      }
+      __syncthreads();
+      const int first = sh_first;
+      // entries before the first singular index are written (sequential loop with break)
+      for (int i = tid; i < first; i += T) {
+        double step = scale * (grad[i] - c) / hess[i];
+        upd[i] = cur[i] - step;
+      }
+      __syncthreads();
+      if (first < K) {
+        decay++;
+        upd = cur;  // VariationalInference.java:471
+        aliased = true;
+        if (decay > 10) break;
+      } else {
+        break;
+      }
+    }
+    double a = 0.0;
+    int kg = 0;
+    for (int i = tid; i < K; i += T) {
+      a += upd[i];
+      if (fabs((upd[i] - cur[i]) / cur[i]) >= (double)0.000001f) kg = 1;
+    }
+    if (tid == 0) sh_flag = 0;
+    block_sum2(a, 0.0, alpha_sum, dummy);
+    if (kg) atomicOr(&sh_flag, 1);
+    __syncthreads();
+    keep_going = sh_flag != 0;
+    __syncthreads();
+    if (iter >= 1000) keep_going = false;
+    if (decay > 10) break;
+    iter++;
+    if (!aliased) {  // alphaVector = alphaVectorUpdate (VariationalInference.java:500)
+      cur = fresh;
+      aliased = true;
+    }
+  }
+  __syncthreads();
+  if (cur != alpha)
+    for (int i = tid; i < K; i += T) alpha[i] = cur[i];
+}
+
+// K3 scalar: updateScalarAlpha (VariationalInference.java:573-625) behind the symmetric wrapper
+// (:295-307): alpha_init = mean(alpha), ss = sum_k alpha_ss_k.  One thread (O(1) work per step).
+__device__ double scalar_alpha_newton(int K, int n_docs, double alpha_init, double ss) {
+  int iter = 0;
+  double a = alpha_init;
+  const double Kd = (double)K, D = (double)n_docs;
+  for (;;) {
+    iter++;
+    if (isnan(a) || isinf(a)) {
+      alpha_init *= 10.0;
+      a = alpha_init;
+    }
+    double sum = a * Kd;
+    double g = D * (Kd * digamma_literal(sum) - Kd * digamma_literal(a)) + ss;
+    double h = D * (Kd * Kd * trigamma_literal(sum) - Kd * trigamma_literal(a));
+    a = exp(log(a) - g / (h * a + g));
+    if (fabs(g) < (double)0.000001f) break;
+    if (iter > 1000) break;
+  }
+  return a;
+}
+__global__ void alpha_scalar_kernel(double *alpha, const double *ss, int K, int n_docs) {
+  __shared__ double res;
+  if (threadIdx.x == 0) {
+    double tot = 0.0, old = 0.0;
+    for (int i = 0; i < K; i++) {
+      tot += ss[i];
+      old += alpha[i];
+    }
+    old /= (double)K;
+    res = scalar_alpha_newton(K, n_docs, old, tot);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K; i += blockDim.x) alpha[i] = res;
+}
+__global__ void alpha_scalar_direct_kernel(int K, int n_docs, double alpha_init, double ss,
+                                           double *out) {
+  *out = scalar_alpha_newton(K, n_docs, alpha_init, ss);
+}
+
+__global__ void eval_special_kernel(int which, int64_t n, const double *x, double *y) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double v = x[i];
+  y[i] = which == 0 ? digamma_literal(v)
+                    : which == 1 ? trigamma_literal(v) : which == 2 ? lgamma(v) : exp_digamma(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency; the Java/ctypes host decides whether to shard)
+// ------------------------------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId_t;
+enum { kNcclSum = 0, kNcclInt64 = 4, kNcclFloat64 = 8 };
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+  int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId_t, int) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  std::string err;
+  bool load() {
+    if (handle) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", "/usr/lib/x86_64-linux-gnu/libnccl.so.2"};
+    for (const char *n : names) {
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) {
+      err = std::string("cannot dlopen libnccl.so.2: ") + dlerror();
+      return false;
+    }
+#define LOADSYM(field, name)                                        \
+  *(void **)(&field) = dlsym(handle, name);                         \
+  if (!field) {                                                     \
+    err = std::string("missing NCCL symbol ") + name;               \
+    return false;                                                   \
+  }
+    LOADSYM(GetUniqueId, "ncclGetUniqueId");
+    LOADSYM(CommInitRank, "ncclCommInitRank");
+    LOADSYM(AllReduce, "ncclAllReduce");
+    LOADSYM(GroupStart, "ncclGroupStart");
+    LOADSYM(GroupEnd, "ncclGroupEnd");
+    LOADSYM(CommDestroy, "ncclCommDestroy");
+    LOADSYM(GetErrorString, "ncclGetErrorString");
+#undef LOADSYM
+    return true;
+  }
+};
+NcclApi g_nccl;
+std::string g_global_error;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct mrlda_ctx {
+  mrlda_config cfg;
+  int K = 0, V = 0, KS = 0;
+  const EstepVariant *variant = nullptr;
+  int num_sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  std::string err;
+  int64_t launches = 0;
+
+  // corpus
+  int64_t D = 0, Z = 0, n_tokens = 0;
+  int64_t *d_row_ptr = nullptr;
+  int32_t *d_term = nullptr, *d_count = nullptr, *d_order = nullptr, *d_tokens = nullptr;
+  double *d_gamma = nullptr;
+  bool gamma_valid = false;
+  int p90_rows = 0, max_rows = 0;
+
+  // model
+  double *d_alpha = nullptr, *d_lik_alpha = nullptr;
+  double *d_logbeta = nullptr, *d_E = nullptr, *d_rowmax = nullptr, *d_dl = nullptr;
+  double *d_stats = nullptr;
+  float *d_nrm = nullptr;
+  uint8_t *d_present = nullptr;
+  bool alpha_set = false, beta_set = false, have_dl = false;
+
+  // per-iteration
+  double *d_alpha_ss = nullptr;   // K
+  long long *d_counters = nullptr; // [0] ll counter, [1] n_docs, [2] n_tokens, [3] slow rows
+  int *d_work = nullptr;           // [0] work queue, [1] slow rows
+  double *d_partial = nullptr, *d_colsum = nullptr, *d_alpha_work = nullptr;
+  int nslabs = 0, slab = 0;
+  int64_t total_docs = 0, total_tokens = 0, terms_seen = 0;
+
+  ncclComm_t comm = nullptr;
+};
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return MRLDA_ECUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+static void set_err(mrlda_ctx *ctx, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  g_global_error = buf;
+}
+
+static const EstepVariant *select_variant(int K) {
+  const EstepVariant *tabs[] = {g_estep_variants_L1, g_estep_variants_L2, g_estep_variants_L4,
+                                g_estep_variants_L8, g_estep_variants_L16, g_estep_variants_L32};
+  const int ns[] = {g_estep_variants_L1_n, g_estep_variants_L2_n, g_estep_variants_L4_n,
+                    g_estep_variants_L8_n, g_estep_variants_L16_n, g_estep_variants_L32_n};
+  const char *force = getenv("MRLDA_ESTEP_VARIANT");  // "L,KPL" — profiling aid
+  int fl = 0, fk = 0;
+  if (force && sscanf(force, "%d,%d", &fl, &fk) != 2) fl = fk = 0;
+  const EstepVariant *best = nullptr;
+  for (int t = 0; t < 6; t++)
+    for (int i = 0; i < ns[t]; i++) {
+      const EstepVariant *v = &tabs[t][i];
+      int ks = v->L * v->KPL;
+      if (ks < K) continue;
+      if (fl && v->L == fl && v->KPL == fk) return v;
+      if (!best || ks < best->L * best->KPL ||
+          (ks == best->L * best->KPL && v->KPL < best->KPL))
+        best = v;
+    }
+  return best;
+}
+
+extern "C" {
+
+const char *mrlda_version(void) { return "mrlda_b200 0.1 (sm_100a, fp64)"; }
+
+void mrlda_default_config(mrlda_config *cfg) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->sweep_cap = 100;  // Settings.java:54
+  cfg->learning = 1;     // Settings.java:46
+  cfg->world_size = 1;
+  cfg->update_alpha = 1;
+  cfg->eta = 1e-12;  // Settings.java:58
+  cfg->seed = 0x4d724c4441ull;
+}
+
+const char *mrlda_last_error(const mrlda_ctx *ctx) {
+  return ctx ? ctx->err.c_str() : g_global_error.c_str();
+}
+
+int64_t mrlda_kernel_launches(const mrlda_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void mrlda_destroy(mrlda_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  void *ptrs[] = {ctx->d_row_ptr, ctx->d_term,   ctx->d_count,    ctx->d_order,  ctx->d_tokens,
+                  ctx->d_gamma,   ctx->d_alpha,  ctx->d_lik_alpha, ctx->d_logbeta, ctx->d_E,
+                  ctx->d_rowmax,  ctx->d_dl,     ctx->d_stats,    ctx->d_nrm,    ctx->d_present,
+                  ctx->d_alpha_ss, ctx->d_counters, ctx->d_work,  ctx->d_partial, ctx->d_colsum,
+                  ctx->d_alpha_work};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  for (auto &e : ctx->ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
+  if (!cfg || !out) {
+    set_err(nullptr, "mrlda_create: null argument");
+    return MRLDA_EINVAL;
+  }
+  *out = nullptr;
+  if (cfg->n_topics <= 0 || cfg->n_terms <= 0 || cfg->sweep_cap < 2 || cfg->world_size < 1 ||
+      cfg->rank < 0 || cfg->rank >= cfg->world_size || !(cfg->eta > 0.0)) {
+    set_err(nullptr, "mrlda_create: invalid config (topics=%d terms=%d sweep_cap=%d rank=%d/%d eta=%g)",
+            cfg->n_topics, cfg->n_terms, cfg->sweep_cap, cfg->rank, cfg->world_size, cfg->eta);
+    return MRLDA_EINVAL;
+  }
+  if (cfg->n_topics > MRLDA_MAX_TOPICS) {
+    set_err(nullptr, "mrlda_create: %d topics exceed the compiled kernel range (max %d)",
+            cfg->n_topics, MRLDA_MAX_TOPICS);
+    return MRLDA_EUNSUPPORTED;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    set_err(nullptr, "mrlda_create: no CUDA device (%s); there is no CPU fallback",
+            cudaGetErrorString(e));
+    return MRLDA_ECUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) {
+    set_err(nullptr, "mrlda_create: device %d out of range (%d devices)", cfg->device, ndev);
+    return MRLDA_EINVAL;
+  }
+  mrlda_ctx *ctx = new mrlda_ctx();
+  ctx->cfg = *cfg;
+  ctx->K = cfg->n_topics;
+  ctx->V = cfg->n_terms;
+  ctx->variant = select_variant(ctx->K);
+  if (!ctx->variant) {
+    set_err(nullptr, "mrlda_create: no E-step kernel variant for %d topics", ctx->K);
+    delete ctx;
+    return MRLDA_EUNSUPPORTED;
+  }
+  ctx->KS = ctx->variant->L * ctx->variant->KPL;
+  auto fail = [&](int code) {
+    g_global_error = ctx->err;
+    mrlda_destroy(ctx);
+    return code;
+  };
+#define CKC(call)                                                                            \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) {                                                                 \
+      set_err(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      return fail(e_ == cudaErrorMemoryAllocation ? MRLDA_ENOMEM : MRLDA_ECUDA);             \
+    }                                                                                        \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major < 10) {
+    set_err(ctx, "mrlda_create: device %d is sm_%d%d; this library is built for sm_100a only",
+            cfg->device, prop.major, prop.minor);
+    return fail(MRLDA_ECUDA);
+  }
+  ctx->num_sms = prop.multiProcessorCount;
+  ctx->smem_optin = prop.sharedMemPerBlockOptin;
+  CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (auto &ev : ctx->ev) CKC(cudaEventCreate(&ev));
+  const size_t K = ctx->K, V = ctx->V, KS = ctx->KS;
+  CKC(cudaMalloc(&ctx->d_alpha, K * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_lik_alpha, sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_logbeta, V * K * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_E, V * KS * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_rowmax, V * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_dl, V * K * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_stats, V * K * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_nrm, K * sizeof(float)));
+  CKC(cudaMalloc(&ctx->d_present, V));
+  CKC(cudaMalloc(&ctx->d_alpha_ss, K * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_counters, 4 * sizeof(long long)));
+  CKC(cudaMalloc(&ctx->d_work, 4 * sizeof(int)));
+  ctx->slab = 256;
+  ctx->nslabs = (int)((V + ctx->slab - 1) / ctx->slab);
+  CKC(cudaMalloc(&ctx->d_partial, (size_t)ctx->nslabs * K * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_colsum, K * sizeof(double)));
+  CKC(cudaMalloc(&ctx->d_alpha_work, 3 * K * sizeof(double)));
+  CKC(cudaMemsetAsync(ctx->d_stats, 0, V * K * sizeof(double), ctx->stream));
+  CKC(cudaMemsetAsync(ctx->d_present, 0, V, ctx->stream));
+  CKC(cudaMemsetAsync(ctx->d_dl, 0, V * K * sizeof(double), ctx->stream));
+  CKC(cudaMemsetAsync(ctx->d_nrm, 0, K * sizeof(float), ctx->stream));
+  CKC(cudaMemsetAsync(ctx->d_alpha_ss, 0, K * sizeof(double), ctx->stream));
+  CKC(cudaStreamSynchronize(ctx->stream));
+#undef CKC
+  *out = ctx;
+  return MRLDA_OK;
+}
+
+static int refresh_rows(mrlda_ctx *ctx) {
+  int threads = 256;
+  int64_t blocks = ((int64_t)ctx->V * 32 + threads - 1) / threads;
+  expand_rows_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_logbeta, ctx->d_E,
+                                                                     ctx->d_rowmax, ctx->V, ctx->K,
+                                                                     ctx->KS);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  return MRLDA_OK;
+}
+
+int mrlda_set_corpus_csr(mrlda_ctx *ctx, int64_t n_docs, const int64_t *row_ptr,
+                         const int32_t *term_id, const int32_t *count, const int32_t *doc_id,
+                         const double *gamma0) {
+  (void)doc_id;  // keys are carried by the host side; the kernels address documents by position
+  if (!ctx) return MRLDA_EINVAL;
+  if (n_docs < 0 || n_docs > 0x7fffffff || !row_ptr || (n_docs > 0 && row_ptr[0] != 0)) {
+    set_err(ctx, "mrlda_set_corpus_csr: bad row_ptr / n_docs");
+    return MRLDA_EINVAL;
+  }
+  const int64_t D = n_docs, Z = row_ptr[D];
+  if (Z < 0 || (Z > 0 && (!term_id || !count))) {
+    set_err(ctx, "mrlda_set_corpus_csr: null term_id/count");
+    return MRLDA_EINVAL;
+  }
+  std::vector<int32_t> tokens((size_t)D), order((size_t)D), nnz((size_t)D);
+  int64_t total_tokens = 0;
+  for (int64_t d = 0; d < D; d++) {
+    int64_t b = row_ptr[d], e = row_ptr[d + 1];
+    if (e < b || e > Z) {
+      set_err(ctx, "mrlda_set_corpus_csr: row_ptr not monotone at document %lld", (long long)d);
+      return MRLDA_EINVAL;
+    }
+    int64_t t = 0;
+    for (int64_t z = b; z < e; z++) {
+      if (term_id[z] < 1 || term_id[z] > ctx->V) {
+        set_err(ctx, "mrlda_set_corpus_csr: term id %d outside [1,%d] (document %lld)", term_id[z],
+                ctx->V, (long long)d);
+        return MRLDA_EINVAL;
+      }
+      if (count[z] <= 0) {
+        set_err(ctx, "mrlda_set_corpus_csr: non-positive count (document %lld)", (long long)d);
+        return MRLDA_EINVAL;
+      }
+      t += count[z];
+    }
+    if (t > 0x7fffffff) {
+      set_err(ctx, "mrlda_set_corpus_csr: document %lld has more than 2^31 tokens", (long long)d);
+      return MRLDA_EINVAL;
+    }
+    tokens[d] = (int32_t)t;
+    nnz[d] = (int32_t)(e - b);
+    total_tokens += t;
+  }
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](int32_t a, int32_t b) { return nnz[a] > nnz[b]; });
+  ctx->max_rows = D ? nnz[order[0]] : 0;
+  ctx->p90_rows = D ? nnz[order[(size_t)(D / 10)]] : 0;
+
+  CK(cudaSetDevice(ctx->cfg.device));
+  void *olds[] = {ctx->d_row_ptr, ctx->d_term, ctx->d_count, ctx->d_order, ctx->d_tokens, ctx->d_gamma};
+  for (void *p : olds)
+    if (p) cudaFree(p);
+  ctx->d_row_ptr = nullptr;
+  ctx->d_term = ctx->d_count = ctx->d_order = ctx->d_tokens = nullptr;
+  ctx->d_gamma = nullptr;
+  const size_t K = ctx->K;
+  CK(cudaMalloc(&ctx->d_row_ptr, (size_t)(D + 1) * sizeof(int64_t)));
+  CK(cudaMalloc(&ctx->d_term, std::max<size_t>(1, (size_t)Z) * sizeof(int32_t)));
+  CK(cudaMalloc(&ctx->d_count, std::max<size_t>(1, (size_t)Z) * sizeof(int32_t)));
+  CK(cudaMalloc(&ctx->d_order, std::max<size_t>(1, (size_t)D) * sizeof(int32_t)));
+  CK(cudaMalloc(&ctx->d_tokens, std::max<size_t>(1, (size_t)D) * sizeof(int32_t)));
+  CK(cudaMalloc(&ctx->d_gamma, std::max<size_t>(1, (size_t)D * K) * sizeof(double)));
+  CK(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, (size_t)(D + 1) * sizeof(int64_t),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  if (Z) {
+    CK(cudaMemcpyAsync(ctx->d_term, term_id, (size_t)Z * sizeof(int32_t), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_count, count, (size_t)Z * sizeof(int32_t), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  }
+  if (D) {
+    CK(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)D * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_tokens, tokens.data(), (size_t)D * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (gamma0 && D) {
+    CK(cudaMemcpyAsync(ctx->d_gamma, gamma0, (size_t)D * K * sizeof(double), cudaMemcpyHostToDevice,
+                       ctx->stream));
+    ctx->gamma_valid = true;
+  } else {
+    CK(cudaMemsetAsync(ctx->d_gamma, 0, std::max<size_t>(1, (size_t)D * K) * sizeof(double),
+                       ctx->stream));
+    ctx->gamma_valid = false;
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->D = D;
+  ctx->Z = Z;
+  ctx->n_tokens = total_tokens;
+  return MRLDA_OK;
+}
+
+int mrlda_set_alpha(mrlda_ctx *ctx, const double *alpha) {
+  if (!ctx || !alpha) return MRLDA_EINVAL;
+  for (int k = 0; k < ctx->K; k++)
+    if (!(alpha[k] > 0.0) || !(alpha[k] < 1e300)) {
+      set_err(ctx, "mrlda_set_alpha: alpha[%d] = %g is not a positive finite number", k, alpha[k]);
+      return MRLDA_EINVAL;
+    }
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(ctx->d_alpha, alpha, (size_t)ctx->K * sizeof(double), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->alpha_set = true;
+  return MRLDA_OK;
+}
+
+int mrlda_get_alpha(mrlda_ctx *ctx, double *alpha) {
+  if (!ctx || !alpha) return MRLDA_EINVAL;
+  if (!ctx->alpha_set) {
+    set_err(ctx, "mrlda_get_alpha: alpha not set");
+    return MRLDA_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(alpha, ctx->d_alpha, (size_t)ctx->K * sizeof(double), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRLDA_OK;
+}
+
+int mrlda_init_beta_random(mrlda_ctx *ctx) {
+  if (!ctx) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int64_t n = (int64_t)ctx->V * ctx->K;
+  init_beta_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+      ctx->d_logbeta, ctx->d_present, 0, ctx->V, ctx->K, ctx->cfg.seed);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  int rc = refresh_rows(ctx);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->beta_set = true;
+  ctx->have_dl = false;
+  return MRLDA_OK;
+}
+
+int mrlda_set_logbeta(mrlda_ctx *ctx, const double *logbeta) {
+  if (!ctx || !logbeta) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(ctx->d_logbeta, logbeta, (size_t)ctx->V * ctx->K * sizeof(double),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  int rc = refresh_rows(ctx);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->beta_set = true;
+  ctx->have_dl = false;
+  return MRLDA_OK;
+}
+
+int mrlda_get_logbeta(mrlda_ctx *ctx, double *logbeta) {
+  if (!ctx || !logbeta) return MRLDA_EINVAL;
+  if (!ctx->beta_set) {
+    set_err(ctx, "mrlda_get_logbeta: beta not set");
+    return MRLDA_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(logbeta, ctx->d_logbeta, (size_t)ctx->V * ctx->K * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRLDA_OK;
+}
+
+int mrlda_set_beta(mrlda_ctx *ctx, const double *digamma_lambda, const float *normaliser,
+                   const uint8_t *present) {
+  if (!ctx || !digamma_lambda || !normaliser || !present) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  const size_t n = (size_t)ctx->V * ctx->K;
+  CK(cudaMemcpyAsync(ctx->d_dl, digamma_lambda, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_nrm, normaliser, (size_t)ctx->K * sizeof(float), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_present, present, (size_t)ctx->V, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  // rows absent from the file: retrieveBeta's lazy initialisation (DocumentMapper.java:450-460)
+  init_beta_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_logbeta, ctx->d_present, 1, ctx->V,
+                                                    ctx->K, ctx->cfg.seed);
+  import_beta_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->d_logbeta, ctx->d_dl, ctx->d_nrm,
+                                                      ctx->d_present, ctx->V, ctx->K);
+  ctx->launches += 2;
+  CK(cudaGetLastError());
+  int rc = refresh_rows(ctx);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->beta_set = true;
+  ctx->have_dl = true;
+  return MRLDA_OK;
+}
+
+int mrlda_get_beta(mrlda_ctx *ctx, double *digamma_lambda, float *normaliser, uint8_t *present) {
+  if (!ctx || !digamma_lambda || !normaliser || !present) return MRLDA_EINVAL;
+  if (!ctx->have_dl) {
+    set_err(ctx, "mrlda_get_beta: no beta in file form (run a learning iteration or mrlda_set_beta)");
+    return MRLDA_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(digamma_lambda, ctx->d_dl, (size_t)ctx->V * ctx->K * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(normaliser, ctx->d_nrm, (size_t)ctx->K * sizeof(float), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaMemcpyAsync(present, ctx->d_present, (size_t)ctx->V, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRLDA_OK;
+}
+
+int mrlda_get_gamma(mrlda_ctx *ctx, double *gamma) {
+  if (!ctx || !gamma) return MRLDA_EINVAL;
+  if (!ctx->d_gamma) {
+    set_err(ctx, "mrlda_get_gamma: corpus not set");
+    return MRLDA_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(gamma, ctx->d_gamma, (size_t)ctx->D * ctx->K * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRLDA_OK;
+}
+
+int mrlda_get_alpha_ss(mrlda_ctx *ctx, double *alpha_ss) {
+  if (!ctx || !alpha_ss) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(alpha_ss, ctx->d_alpha_ss, (size_t)ctx->K * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRLDA_OK;
+}
+
+int mrlda_get_stats(mrlda_ctx *ctx, double *stats) {
+  if (!ctx || !stats) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(stats, ctx->d_stats, (size_t)ctx->V * ctx->K * sizeof(double),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRLDA_OK;
+}
+
+// Launch geometry of K1 for the resident corpus: CTAs per SM, threads per CTA, tile rows.
+static void plan_estep(mrlda_ctx *ctx, int *ctas_per_sm, int *threads, int *cap_rows, size_t *smem) {
+  const EstepVariant *v = ctx->variant;
+  const int rpb = 32 / v->L;
+  const int gran = rpb < 2 ? 2 : rpb;  // tile rows: multiple of RPB and even (16-byte alignment)
+  const size_t sm_total = 233472;      // 228 KB per SM, 1 KB reserved per resident CTA
+  const int want = std::max(ctx->p90_rows, gran);
+  int best_c = 1;
+  const char *fc = getenv("MRLDA_ESTEP_CTAS_PER_SM");
+  const int forced = fc ? atoi(fc) : 0;
+  for (int c = 8; c >= 1; c--) {
+    if (forced && c != forced) continue;
+    int t = (v->max_threads / c) & ~31;
+    if (t < 64 && c != 1 && !forced) continue;
+    if (t < 32) continue;
+    size_t per = std::min((sm_total - (size_t)c * 1024) / c, ctx->smem_optin) & ~(size_t)15;
+    size_t fixed = v->smem_bytes(t / 32, 0);
+    if (per <= fixed) continue;
+    int cap = (int)((per - fixed) / ((size_t)ctx->KS * 8 + 8));
+    cap = cap / gran * gran;
+    if (cap < gran) continue;
+    if (cap >= want || c == 1 || forced) {
+      best_c = c;
+      break;
+    }
+  }
+  int c = best_c;
+  int t = std::max(32, (v->max_threads / c) & ~31);
+  size_t per = std::min((sm_total - (size_t)c * 1024) / c, ctx->smem_optin) & ~(size_t)15;
+  size_t fixed = v->smem_bytes(t / 32, 0);
+  int cap = per > fixed ? (int)((per - fixed) / ((size_t)ctx->KS * 8 + 8)) : 0;
+  cap = cap / gran * gran;
+  int need = (std::max(ctx->max_rows, 1) + gran - 1) / gran * gran;
+  if (cap > need) cap = need;  // do not reserve more than the longest document needs
+  if (cap < gran) cap = gran;
+  *ctas_per_sm = c;
+  *threads = t;
+  *cap_rows = cap;
+  *smem = v->smem_bytes(t / 32, cap);
+}
+
+static int exchange(mrlda_ctx *ctx) {
+  if (ctx->cfg.world_size <= 1) return MRLDA_OK;
+  if (!ctx->comm) {
+    set_err(ctx, "world_size %d but mrlda_comm_init was not called", ctx->cfg.world_size);
+    return MRLDA_ESTATE;
+  }
+  int rc = g_nccl.GroupStart();
+  if (!rc && ctx->cfg.learning)
+    rc = g_nccl.AllReduce(ctx->d_stats, ctx->d_stats, (size_t)ctx->V * ctx->K, kNcclFloat64,
+                          kNcclSum, ctx->comm, ctx->stream);
+  if (!rc)
+    rc = g_nccl.AllReduce(ctx->d_alpha_ss, ctx->d_alpha_ss, (size_t)ctx->K, kNcclFloat64, kNcclSum,
+                          ctx->comm, ctx->stream);
+  if (!rc)
+    rc = g_nccl.AllReduce(ctx->d_counters, ctx->d_counters, 4, kNcclInt64, kNcclSum, ctx->comm,
+                          ctx->stream);
+  int rc2 = g_nccl.GroupEnd();
+  if (rc || rc2) {
+    set_err(ctx, "NCCL all-reduce failed: %s", g_nccl.GetErrorString(rc ? rc : rc2));
+    return MRLDA_ENCCL;
+  }
+  return MRLDA_OK;
+}
+
+int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
+  if (!ctx) return MRLDA_EINVAL;
+  if (!ctx->d_row_ptr || !ctx->alpha_set || !ctx->beta_set) {
+    set_err(ctx, "mrlda_e_step: %s not set", !ctx->d_row_ptr ? "corpus" : !ctx->alpha_set ? "alpha" : "beta");
+    return MRLDA_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = ctx->stream;
+  const int K = ctx->K;
+  int launches0 = (int)ctx->launches;
+  CK(cudaEventRecord(ctx->ev[0], st));
+  prep_kernel<<<1, 256, 0, st>>>(ctx->d_alpha, K, ctx->d_lik_alpha);
+  ctx->launches++;
+  if (ctx->cfg.learning) CK(cudaMemsetAsync(ctx->d_stats, 0, (size_t)ctx->V * K * sizeof(double), st));
+  CK(cudaMemsetAsync(ctx->d_alpha_ss, 0, (size_t)K * sizeof(double), st));
+  long long hc[4] = {0, (long long)ctx->D, (long long)ctx->n_tokens, 0};
+  CK(cudaMemcpyAsync(ctx->d_counters, hc, sizeof hc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(int), st));
+
+  int c, t, cap;
+  size_t smem;
+  plan_estep(ctx, &c, &t, &cap, &smem);
+  CK(ctx->variant->prepare(smem));
+  EstepArgs a;
+  a.row_ptr = ctx->d_row_ptr;
+  a.term_id = ctx->d_term;
+  a.count = ctx->d_count;
+  a.doc_order = ctx->d_order;
+  a.doc_tokens = ctx->d_tokens;
+  a.n_docs = ctx->D;
+  a.E = ctx->d_E;
+  a.rowmax = ctx->d_rowmax;
+  a.logbeta = ctx->d_logbeta;
+  a.alpha = ctx->d_alpha;
+  a.lik_alpha = ctx->d_lik_alpha;
+  a.gamma = ctx->d_gamma;
+  a.stats = ctx->cfg.learning ? ctx->d_stats : nullptr;
+  a.alpha_ss = ctx->d_alpha_ss;
+  a.ll_counter = reinterpret_cast<unsigned long long *>(ctx->d_counters);
+  a.work_counter = ctx->d_work;
+  a.slow_rows = ctx->d_work + 1;
+  a.K = K;
+  a.sweeps = ctx->cfg.sweep_cap - 1;
+  a.use_stored_gamma = (ctx->gamma_valid && !ctx->cfg.random_start) ? 1 : 0;
+  a.learning = ctx->cfg.learning ? 1 : 0;
+  a.cap_rows = cap;
+  int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, std::max<int64_t>(ctx->D, 1));
+  CK(cudaEventRecord(ctx->ev[1], st));
+  if (ctx->D > 0) {
+    CK(ctx->variant->launch(a, grid, t, cap, st));
+    ctx->launches++;
+  }
+  CK(cudaEventRecord(ctx->ev[2], st));
+  int rc = exchange(ctx);
+  if (rc) return rc;
+  CK(cudaEventRecord(ctx->ev[3], st));
+  long long hres[4];
+  int hwork[4];
+  CK(cudaMemcpyAsync(hres, ctx->d_counters, sizeof hres, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(hwork, ctx->d_work, sizeof hwork, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  // the reference keeps the gamma it wrote as the next iteration's input unless -randomstart in
+  // training mode suppresses the gamma output (DocumentMapper.java:342, VI.java:232,359)
+  ctx->gamma_valid = true;
+  ctx->total_docs = hres[1];
+  ctx->total_tokens = hres[2];
+  if (out) {
+    float ms = 0.f;
+    memset(out, 0, sizeof *out);
+    out->ll_counter = hres[0];
+    out->log_likelihood = -(double)hres[0] * 1.0 / 1e6;  // VariationalInference.java:261-262
+    out->n_docs = hres[1];
+    out->n_tokens = hres[2];
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+    out->e_step_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+    out->allreduce_ms = ctx->cfg.world_size > 1 ? ms : 0.0;
+    out->estep_launches = (int)ctx->launches - launches0;
+    out->total_launches = out->estep_launches;
+    out->slow_path_rows = hwork[1];
+  }
+  return MRLDA_OK;
+}
+
+int mrlda_m_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
+  if (!ctx) return MRLDA_EINVAL;
+  if (!ctx->cfg.learning) {
+    set_err(ctx, "mrlda_m_step: context is in test mode (learning == 0)");
+    return MRLDA_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = ctx->stream;
+  const int K = ctx->K, V = ctx->V;
+  int launches0 = (int)ctx->launches;
+  CK(cudaEventRecord(ctx->ev[4], st));
+  finalize_colsum_kernel<<<ctx->nslabs, 256, ctx->slab * sizeof(double), st>>>(
+      ctx->d_stats, V, K, ctx->cfg.eta, ctx->slab, ctx->d_partial, ctx->d_present);
+  finalize_norm_kernel<<<(K + 127) / 128, 128, 0, st>>>(ctx->d_partial, ctx->nslabs, K, ctx->d_nrm,
+                                                        ctx->d_colsum);
+  {
+    int threads = 256;
+    int64_t blocks = ((int64_t)V * 32 + threads - 1) / threads;
+    finalize_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(ctx->d_stats, ctx->d_present,
+                                                                ctx->d_nrm, ctx->cfg.eta, V, K,
+                                                                ctx->KS, ctx->d_dl, ctx->d_logbeta,
+                                                                ctx->d_E, ctx->d_rowmax);
+  }
+  ctx->launches += 3;
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev[5], st));
+  if (ctx->cfg.update_alpha) {
+    if (ctx->total_docs > 0x7fffffff) {
+      set_err(ctx, "mrlda_m_step: document count exceeds int (VariationalInference.java:265 casts to int)");
+      return MRLDA_EINVAL;
+    }
+    if (ctx->cfg.symmetric_alpha)
+      alpha_scalar_kernel<<<1, 256, 0, st>>>(ctx->d_alpha, ctx->d_alpha_ss, K, (int)ctx->total_docs);
+    else
+      alpha_vector_kernel<<<1, 256, 0, st>>>(ctx->d_alpha, ctx->d_alpha_ss, K, (int)ctx->total_docs,
+                                             ctx->d_alpha_work);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
+  CK(cudaEventRecord(ctx->ev[6], st));
+  std::vector<uint8_t> pres((size_t)V);
+  CK(cudaMemcpyAsync(pres.data(), ctx->d_present, (size_t)V, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  int64_t seen = 0;
+  for (int v = 0; v < V; v++) seen += pres[v];
+  ctx->terms_seen = seen;
+  ctx->have_dl = true;
+  if (out) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+    out->m_step_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+    out->alpha_ms = ms;
+    out->n_terms_seen = seen;  // TOTAL_TERMS / K (VariationalInference.java:267)
+    out->total_launches += (int)ctx->launches - launches0;
+  }
+  return MRLDA_OK;
+}
+
+int mrlda_iterate(mrlda_ctx *ctx, mrlda_iter_result *out) {
+  mrlda_iter_result tmp;
+  mrlda_iter_result *r = out ? out : &tmp;
+  int rc = mrlda_e_step(ctx, r);
+  if (rc) return rc;
+  if (ctx->cfg.learning) rc = mrlda_m_step(ctx, r);
+  return rc;
+}
+
+int mrlda_update_vector_alpha(mrlda_ctx *ctx, int32_t n_topics, int32_t n_docs,
+                              const double *alpha_in, const double *alpha_ss, double *alpha_out) {
+  if (!ctx || !alpha_in || !alpha_ss || !alpha_out || n_topics <= 0) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  double *buf = nullptr;
+  const size_t K = (size_t)n_topics;
+  CK(cudaMalloc(&buf, 5 * K * sizeof(double)));
+  cudaMemcpyAsync(buf, alpha_in, K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(buf + K, alpha_ss, K * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  alpha_vector_kernel<<<1, 256, 0, ctx->stream>>>(buf, buf + K, n_topics, n_docs, buf + 2 * K);
+  ctx->launches++;
+  cudaMemcpyAsync(alpha_out, buf, K * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(buf);
+  CK(e);
+  return MRLDA_OK;
+}
+
+int mrlda_update_scalar_alpha(mrlda_ctx *ctx, int32_t n_topics, int32_t n_docs, double alpha_init,
+                              double alpha_ss_total, double *alpha_out) {
+  if (!ctx || !alpha_out || n_topics <= 0) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  double *buf = nullptr;
+  CK(cudaMalloc(&buf, sizeof(double)));
+  alpha_scalar_direct_kernel<<<1, 1, 0, ctx->stream>>>(n_topics, n_docs, alpha_init, alpha_ss_total, buf);
+  ctx->launches++;
+  cudaMemcpyAsync(alpha_out, buf, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(buf);
+  CK(e);
+  return MRLDA_OK;
+}
+
+int mrlda_eval_special(mrlda_ctx *ctx, int32_t which, int64_t n, const double *x, double *y) {
+  if (!ctx || !x || !y || n < 0 || which < 0 || which > 3) return MRLDA_EINVAL;
+  if (n == 0) return MRLDA_OK;
+  CK(cudaSetDevice(ctx->cfg.device));
+  double *buf = nullptr;
+  CK(cudaMalloc(&buf, 2 * (size_t)n * sizeof(double)));
+  cudaMemcpyAsync(buf, x, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  eval_special_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(which, n, buf, buf + n);
+  ctx->launches++;
+  cudaMemcpyAsync(y, buf + n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(buf);
+  CK(e);
+  return MRLDA_OK;
+}
+
+int mrlda_nccl_unique_id(uint8_t id[MRLDA_NCCL_ID_BYTES]) {
+  if (!id) return MRLDA_EINVAL;
+  if (!g_nccl.load()) {
+    set_err(nullptr, "%s", g_nccl.err.c_str());
+    return MRLDA_ENCCL;
+  }
+  ncclUniqueId_t u;
+  int rc = g_nccl.GetUniqueId(&u);
+  if (rc) {
+    set_err(nullptr, "ncclGetUniqueId: %s", g_nccl.GetErrorString(rc));
+    return MRLDA_ENCCL;
+  }
+  memcpy(id, u.internal, MRLDA_NCCL_ID_BYTES);
+  return MRLDA_OK;
+}
+
+int mrlda_comm_init(mrlda_ctx *ctx, const uint8_t id[MRLDA_NCCL_ID_BYTES]) {
+  if (!ctx || !id) return MRLDA_EINVAL;
+  if (ctx->cfg.world_size <= 1) return MRLDA_OK;
+  if (!g_nccl.load()) {
+    set_err(ctx, "%s", g_nccl.err.c_str());
+    return MRLDA_ENCCL;
+  }
+  CK(cudaSetDevice(ctx->cfg.device));
+  ncclUniqueId_t u;
+  memcpy(u.internal, id, MRLDA_NCCL_ID_BYTES);
+  int rc = g_nccl.CommInitRank(&ctx->comm, ctx->cfg.world_size, u, ctx->cfg.rank);
+  if (rc) {
+    set_err(ctx, "ncclCommInitRank: %s", g_nccl.GetErrorString(rc));
+    ctx->comm = nullptr;
+    return MRLDA_ENCCL;
+  }
+  return MRLDA_OK;
+}
+
+}  // extern "C"

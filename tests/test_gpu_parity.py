@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): per-iteration ELBO and logbeta within 1e-9 relative in fp64;
+integer bookkeeping (doc/term counts, presence) bit-exact.  The ELBO counter is the int64 sum of
+per-document truncations (DocumentMapper.java:253-254); a 1-ulp difference in a document's
+likelihood can move one truncation by one unit (1e-6), so counters are compared within D units and
+the decoded likelihood within 1e-9 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import rel_err, small_corpus
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+
+
+def _ctx(capi, c, **kw):
+    return capi.Context(c.n_topics, c.n_terms, **kw)
+
+
+def _run_pair(capi, oracle, c, alpha, logbeta, gamma0=None, **cfg):
+    K, V = c.n_topics, c.n_terms
+    with _ctx(capi, c, **cfg) as ctx:
+        ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count, gamma0=gamma0)
+        ctx.set_alpha(alpha)
+        ctx.set_logbeta(logbeta)
+        r = ctx.iterate()
+        out = dict(r=r, gamma=ctx.get_gamma(), alpha_ss=ctx.get_alpha_ss())
+        if cfg.get("learning", 1):
+            out.update(alpha=ctx.get_alpha(), logbeta=ctx.get_logbeta(), beta=ctx.get_beta(),
+                       stats=ctx.get_stats())
+    ref = oracle.iterate(K, V, c.row_ptr, c.term_id, c.count, logbeta, alpha, gamma=gamma0,
+                         random_start=bool(cfg.get("random_start", 0)),
+                         learning=bool(cfg.get("learning", 1)),
+                         symmetric=bool(cfg.get("symmetric_alpha", 0)),
+                         sweeps=cfg.get("sweep_cap", 100) - 1)
+    return out, ref
+
+
+def _check(out, ref, c, learning=True):
+    D = c.n_docs
+    assert out["r"]["n_docs"] == D
+    assert out["r"]["n_tokens"] == c.n_tokens
+    assert abs(out["r"]["ll_counter"] - ref["counter"]) <= D
+    assert abs(out["r"]["log_likelihood"] - ref["log_likelihood"]) <= TOL * abs(ref["log_likelihood"])
+    nz = np.diff(c.row_ptr) > 0
+    assert rel_err(out["gamma"][nz], ref["gamma"][nz]) < TOL
+    assert rel_err(out["alpha_ss"], ref["alpha_ss"]) < TOL
+    if learning:
+        assert out["r"]["n_terms_seen"] == ref["n_terms_seen"]
+        dl, nm, pr = out["beta"]
+        assert np.array_equal(pr, ref["present"])
+        seen = pr.astype(bool)
+        assert np.array_equal(nm, ref["normaliser"])  # (float) cast, TermReducer.java:173
+        assert rel_err(dl[seen], ref["digamma_lambda"][seen]) < TOL
+        assert rel_err(out["logbeta"][seen], ref["logbeta"][seen]) < TOL
+        assert rel_err(out["alpha"], ref["alpha"]) < TOL
+
+
+@pytest.mark.parametrize("K", [3, 8, 20, 33, 50, 100, 130, 200])
+def test_one_iteration_matches_oracle(capi, oracle, K):
+    from mrlda_b200 import corpus
+    c = small_corpus(D=40, V=400, K=K, mean_len=50, seed=K)
+    alpha = np.full(K, 1e-3)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=K + 1)
+    out, ref = _run_pair(capi, oracle, c, alpha, lb)
+    _check(out, ref, c)
+    assert out["r"]["total_launches"] >= 5
+
+
+def test_large_k_variants(capi, oracle):
+    from mrlda_b200 import corpus
+    for K in (300, 600, 1000):
+        c = small_corpus(D=6, V=150, K=K, mean_len=30, seed=K)
+        alpha = np.full(K, 1e-3)
+        lb = corpus.init_logbeta(c.n_terms, K, seed=5)
+        out, ref = _run_pair(capi, oracle, c, alpha, lb, sweep_cap=12)
+        _check(out, ref, c)
+
+
+def test_stats_are_phi_weighted_counts(capi, oracle):
+    """sum_k stats[v][k] = total count of term v (sum_k phi = 1), and stats match exp(log_phi)."""
+    from mrlda_b200 import corpus
+    K = 8
+    c = small_corpus(D=50, V=200, K=K, seed=3)
+    alpha = np.full(K, 0.1)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=9)
+    out, _ = _run_pair(capi, oracle, c, alpha, lb)
+    tot = np.bincount(c.term_id - 1, weights=c.count, minlength=c.n_terms)
+    assert np.allclose(out["stats"].sum(1), tot, rtol=1e-12, atol=1e-12)
+    e = oracle.estep(K, c.row_ptr, c.term_id, c.count, lb, alpha, want_log_phi=True)
+    ref_stats = np.zeros((c.n_terms, K))
+    np.add.at(ref_stats, c.term_id - 1, np.exp(e["log_phi"]))
+    big = ref_stats > 1e-200
+    assert rel_err(out["stats"][big], ref_stats[big]) < TOL
+    # gamma conservation: sum_k gamma = sum_k alpha + N_d
+    ntok = np.add.reduceat(c.count, c.row_ptr[:-1])
+    assert np.allclose(out["gamma"].sum(1), alpha.sum() + ntok, rtol=1e-12)
+
+
+def test_stored_gamma_and_random_start(capi, oracle):
+    from mrlda_b200 import corpus
+    K = 20
+    c = small_corpus(D=30, V=300, K=K, seed=4)
+    alpha = np.full(K, 0.05)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=2)
+    rng = np.random.default_rng(0)
+    g0 = rng.gamma(1.0, 2.0, size=(c.n_docs, K)) + 0.01
+    out, ref = _run_pair(capi, oracle, c, alpha, lb, gamma0=g0, sweep_cap=20)
+    _check(out, ref, c)
+    out2, ref2 = _run_pair(capi, oracle, c, alpha, lb, gamma0=g0, sweep_cap=20, random_start=1)
+    _check(out2, ref2, c)
+    assert rel_err(out["gamma"], out2["gamma"]) > 1e-6  # the stored gamma really was used
+
+
+def test_test_mode_runs_e_step_only(capi, oracle):
+    from mrlda_b200 import corpus
+    K = 8
+    c = small_corpus(D=25, V=200, K=K, seed=6)
+    alpha = np.full(K, 0.2)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=3)
+    out, ref = _run_pair(capi, oracle, c, alpha, lb, learning=0)
+    _check(out, ref, c, learning=False)
+    assert out["r"]["n_terms_seen"] == 0
+
+
+def test_symmetric_alpha_iteration(capi, oracle):
+    from mrlda_b200 import corpus
+    K = 20
+    c = small_corpus(D=80, V=300, K=K, seed=8)
+    alpha = np.full(K, 1e-3)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=4)
+    out, ref = _run_pair(capi, oracle, c, alpha, lb, symmetric_alpha=1)
+    _check(out, ref, c)
+    assert np.all(out["alpha"] == out["alpha"][0])
+
+
+def test_empty_and_single_token_documents(capi, oracle):
+    """null content is counted and skipped (DocumentMapper.java:178,197-201); 1-token documents."""
+    from mrlda_b200 import corpus
+    K, V = 8, 50
+    docs = [{1: 3, 7: 1}, None, {5: 1}, {}, {50: 2, 49: 1, 1: 1}, {2: 1}]
+    c = corpus.from_docs(docs, V, K)
+    alpha = np.full(K, 1e-3)
+    lb = corpus.init_logbeta(V, K, seed=1)
+    out, ref = _run_pair(capi, oracle, c, alpha, lb)
+    _check(out, ref, c)
+    assert out["r"]["n_docs"] == 6
+
+
+def test_long_documents_exceed_the_tile(capi, oracle):
+    """Documents with more distinct terms than the shared-memory tile holds stream rows from L2."""
+    from mrlda_b200 import corpus
+    K = 200
+    c = corpus.generate(6, 3000, K, 1500, seed=11)
+    assert np.diff(c.row_ptr).max() > 200
+    alpha = np.full(K, 1e-3)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=7)
+    out, ref = _run_pair(capi, oracle, c, alpha, lb, sweep_cap=8)
+    _check(out, ref, c)
+
+
+def test_sparse_beta_takes_exact_slow_path(capi, oracle):
+    """A model where most (topic,term) cells are dead (lambda = eta => logbeta ~ -1e12) and the
+    stored gamma points at the wrong topics: the linear-space norm underflows and the kernel must
+    redo those rows in log space without NaNs."""
+    K, V, D = 8, 40, 12
+    rng = np.random.default_rng(5)
+    from mrlda_b200 import corpus
+    lb = np.full((V, K), -1.0e12)
+    owner = rng.integers(0, K, size=V)
+    lb[np.arange(V), owner] = np.log(rng.random(V) + 0.1)
+    docs = []
+    for d in range(D):
+        terms = rng.choice(V, size=6, replace=False) + 1
+        docs.append({int(t): int(rng.integers(1, 4)) for t in terms})
+    c = corpus.from_docs(docs, V, K)
+    alpha = np.full(K, 1e-3)
+    g0 = np.full((D, K), 1e-3)
+    g0[:, 0] = 30.0  # all mass on topic 0; theta_k underflows for k != 0
+    out, ref = _run_pair(capi, oracle, c, alpha, lb, gamma0=g0, sweep_cap=6)
+    assert np.all(np.isfinite(out["gamma"]))
+    assert out["r"]["slow_path_rows"] > 0
+    _check(out, ref, c)
+
+
+def test_three_em_iterations_track_oracle(capi, oracle):
+    """Per-iteration ELBO / logbeta / alpha parity over consecutive iterations (gamma carried)."""
+    from mrlda_b200 import corpus
+    K = 20
+    c = small_corpus(D=120, V=500, K=K, mean_len=60, seed=12)
+    alpha = np.full(K, 1e-3)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=13)
+    gamma = None
+    a_ref, lb_ref = alpha.copy(), lb.copy()
+    with capi.Context(K, c.n_terms) as ctx:
+        ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count)
+        ctx.set_alpha(alpha)
+        ctx.set_logbeta(lb)
+        for it in range(3):
+            r = ctx.iterate()
+            ref = oracle.iterate(K, c.n_terms, c.row_ptr, c.term_id, c.count, lb_ref, a_ref,
+                                 gamma=gamma)
+            assert abs(r["log_likelihood"] - ref["log_likelihood"]) <= TOL * abs(ref["log_likelihood"]), it
+            seen = ref["present"].astype(bool)
+            assert rel_err(ctx.get_logbeta()[seen], ref["logbeta"][seen]) < 10 * TOL, it
+            assert rel_err(ctx.get_alpha(), ref["alpha"]) < 10 * TOL, it
+            assert rel_err(ctx.get_gamma(), ref["gamma"]) < 10 * TOL, it
+            gamma, a_ref = ref["gamma"], ref["alpha"]
+            lb_ref = np.where(seen[:, None], ref["logbeta"], lb_ref)
+
+
+def test_alpha_known_answers_on_device(capi):
+    """The reference's own KATs (VariationalInferenceTest.java:27-62) through the device kernels."""
+    with capi.Context(3, 10) as ctx:
+        out = ctx.update_vector_alpha(
+            3, 112, [0.4736839726180464, 9.928726975283879, 8.319361678447014],
+            [-23792.9569126969113, -22519.9434073184025, -23973.2360888324797])
+        want = [0.4736839726180464, 9.92872697528388, 8.319361678447015]
+        assert np.max(np.abs(out - want)) < 1e-10
+        kats = [(5, -40100.9192398908126052, 0.2958548131184747),
+                (5, -34828.2371112336259102, 0.3731832583179411),
+                (5, -37309.1699276268700487, 0.3319329678764105),
+                (5, -44085.8660385293114814, 0.2568195157403902),
+                (10, -155990.5727383689954877, 0.1531475153565107),
+                (10, -196359.2521305996051524, 0.1150183709445565),
+                (10, -226577.3570433593704365, 0.0972395316113154),
+                (10, -256318.9209672076685820, 0.0845206104885002)]
+        for K, ss, want in kats:
+            assert abs(ctx.update_scalar_alpha(K, 2246, 100, ss) - want) < 1e-10
+
+
+def test_device_special_functions_match_oracle(capi, oracle):
+    x = np.concatenate([np.logspace(-12, 6, 400), [1e-3, 1.0, 1.4616321449683623, 2.5]])
+    with capi.Context(3, 10) as ctx:
+        dg = ctx.eval_special("digamma", x)
+        tg = ctx.eval_special("trigamma", x)
+        lg = ctx.eval_special("lngamma", x)
+        ed = ctx.eval_special("exp_digamma", x)
+    want_dg = np.array([oracle.digamma(v) for v in x])
+    assert np.array_equal(dg, want_dg) or rel_err(dg, want_dg) < 1e-13
+    assert rel_err(tg, [oracle.trigamma(v) for v in x]) < 1e-13
+    lgw = np.array([oracle.lngamma(v) for v in x])
+    assert np.max(np.abs(lg - lgw) / np.maximum(np.abs(lgw), 1.0)) < 1e-13
+    big = x > 2e-3  # below, exp(digamma) underflows towards 0
+    assert rel_err(ed[big], np.exp(want_dg[big])) < 1e-12
+
+
+def test_error_paths(capi):
+    with pytest.raises(capi.MrldaError):
+        capi.Context(0, 10)
+    with pytest.raises(capi.MrldaError):
+        capi.Context(5000, 10)
+    with capi.Context(4, 10) as ctx:
+        with pytest.raises(capi.MrldaError):
+            ctx.iterate()  # nothing set
+        with pytest.raises(capi.MrldaError):
+            ctx.set_corpus_csr([0, 1], [11], [1])  # term id out of range
+        with pytest.raises(capi.MrldaError):
+            ctx.set_alpha([0.1, 0.0, 0.1, 0.1])
