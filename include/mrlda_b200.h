@@ -156,6 +156,10 @@ int mrlda_eval_special(mrlda_ctx *ctx, int32_t which /*0 digamma,1 trigamma,2 ln
 int mrlda_nccl_unique_id(uint8_t id[MRLDA_NCCL_ID_BYTES]);
 int mrlda_comm_init(mrlda_ctx *ctx, const uint8_t id[MRLDA_NCCL_ID_BYTES]);
 
+/* Measured DFMA throughput of the device (TFLOP/s), the second roofline denominator bench.py
+ * reports: at the reference's fixed 99 sweeps the E-step is FP64-pipe bound. */
+int mrlda_measure_fp64_peak(mrlda_ctx *ctx, double *tflops);
+
 /* Number of this library's kernels launched on the context since creation. */
 int64_t mrlda_kernel_launches(const mrlda_ctx *ctx);
 /* Library/build description, e.g. "mrlda_b200 0.1 sm_100a". */

@@ -326,6 +326,21 @@ __global__ void eval_special_kernel(int which, int64_t n, const double *x, doubl
                     : which == 1 ? trigamma_literal(v) : which == 2 ? lgamma(v) : exp_digamma(v);
 }
 
+
+// DFMA throughput probe: the E-step is bound by the FP64 pipe, not HBM, so
+// bench.py reports its flop rate against this measured peak next to the HBM roofline.
+__global__ void fp64_peak_kernel(double *out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 123.456) out[0] = s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // NCCL through dlopen (no link-time dependency; the Java/ctypes host decides whether to shard)
 // ------------------------------------------------------------------------------------------------
@@ -1098,6 +1113,29 @@ int mrlda_eval_special(mrlda_ctx *ctx, int32_t which, int64_t n, const double *x
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   cudaFree(buf);
   CK(e);
+  return MRLDA_OK;
+}
+
+int mrlda_measure_fp64_peak(mrlda_ctx *ctx, double *tflops) {
+  if (!ctx || !tflops) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  double *buf = nullptr;
+  CK(cudaMalloc(&buf, sizeof(double)));
+  const int iters = 1 << 16, threads = 256, grid = ctx->num_sms * 8;
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    fp64_peak_kernel<<<grid, threads, 0, ctx->stream>>>(buf, iters, 1.0 + rep);
+    ctx->launches++;
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    double fl = 2.0 * 8.0 * (double)iters * threads * (double)grid;
+    if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaFree(buf);
+  *tflops = best;
   return MRLDA_OK;
 }
 
