@@ -89,14 +89,14 @@ def cpu_reference_rate(c, logbeta, alpha, target_s=15.0):
     from oracle import oracle as O
     cores = O.num_threads()
     D = c.n_docs
-    pilot = min(D, max(cores, 8))
+    pilot = min(D, 4 * max(cores, 8))
     sub = c.slice_docs(0, pilot)
+    O.estep(c.n_topics, sub.row_ptr, sub.term_id, sub.count, logbeta, alpha)  # thread-pool warm-up
     t0 = time.perf_counter()
     O.estep(c.n_topics, sub.row_ptr, sub.term_id, sub.count, logbeta, alpha)
     dt = max(time.perf_counter() - t0, 1e-3)
     n = int(min(D, max(pilot, pilot * target_s / dt)))
-    n = max(cores, n // cores * cores)
-    n = min(n, D)
+    n = min(max(cores, n // cores * cores), D)
     sub = c.slice_docs(0, n)
     t0 = time.perf_counter()
     O.estep(c.n_topics, sub.row_ptr, sub.term_id, sub.count, logbeta, alpha)

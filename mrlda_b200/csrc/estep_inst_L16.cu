@@ -3,6 +3,8 @@
 
 namespace mrlda {
 const EstepVariant g_estep_variants_L16[] = {
+    MRLDA_VARIANT(16, 14),
+    MRLDA_VARIANT(16, 16),
     MRLDA_VARIANT(16, 18),
     MRLDA_VARIANT(16, 20),
     MRLDA_VARIANT(16, 22),
@@ -12,5 +14,5 @@ const EstepVariant g_estep_variants_L16[] = {
     MRLDA_VARIANT(16, 30),
     MRLDA_VARIANT(16, 32),
 };
-const int g_estep_variants_L16_n = 8;
+const int g_estep_variants_L16_n = 10;
 }  // namespace mrlda

@@ -3,6 +3,7 @@
 
 namespace mrlda {
 const EstepVariant g_estep_variants_L8[] = {
+    MRLDA_VARIANT(8, 14),
     MRLDA_VARIANT(8, 16),
     MRLDA_VARIANT(8, 18),
     MRLDA_VARIANT(8, 20),
@@ -13,5 +14,5 @@ const EstepVariant g_estep_variants_L8[] = {
     MRLDA_VARIANT(8, 30),
     MRLDA_VARIANT(8, 32),
 };
-const int g_estep_variants_L8_n = 9;
+const int g_estep_variants_L8_n = 10;
 }  // namespace mrlda

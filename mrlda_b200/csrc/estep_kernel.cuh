@@ -69,6 +69,8 @@ struct EstepShape {
   static constexpr int KS = L * KPL;
   static constexpr int HALF = KPL / 2;
   static constexpr int MAX_THREADS = KPL <= 22 ? 384 : 256;  // 168 vs 255 registers per thread
+  // row blocks in flight per warp: as many as the register budget allows (3*KPL + U*KPL doubles)
+  static constexpr int UNROLL = (KPL <= 14) ? 2 : ((KPL >= 24 && KPL <= 26) ? 2 : 1);
   static_assert(KPL % 2 == 0, "KPL must be even (16-byte units)");
   static_assert(L >= 8 || (KPL / 2) % 2 == 1, "KPL must be 2*odd for L < 8 (bank-conflict-free rows)");
 };
@@ -127,11 +129,143 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// One sweep's pass over the rows owned by this warp: U row blocks (RPB rows each) are processed
+// together so that their load -> DFMA -> shuffle -> reciprocal chains overlap.  LAST adds the
+// likelihood terms and the statistics scatter (DocumentMapper.java:421,315-329).
+template <int L, int KPL, int U, bool LAST>
+__device__ __forceinline__ void sweep_rows(const EstepArgs &a, const double *tile,
+                                           const double *cnt_s, const double *gam_s,
+                                           double *gextra_s, const double (&th)[KPL],
+                                           double (&s)[KPL], double &lik, const int64_t b,
+                                           const int n, const int cap, const int nblocks,
+                                           const int warp, const int NW, const int lane) {
+  constexpr int RPB = 32 / L, KS = L * KPL, HALF = KPL / 2;
+  const int g = lane / L, j = lane % L;
+  const int K = a.K;
+  for (int rb0 = warp; rb0 < nblocks; rb0 += U * NW) {
+    double e[U][KPL];
+    double cw[U], dot[U];
+    bool valid[U];
+    int rbu[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      int rb = rb0 + u * NW;
+      const bool active = rb < nblocks;  // warp-uniform
+      rb = active ? rb : nblocks - 1;
+      rbu[u] = rb;
+      const int w = rb * RPB + g;
+      valid[u] = active && w < n;
+      const int wc = w < n ? w : n - 1;
+      if (rb * RPB < cap) {  // warp-uniform: rows resident in the tile
+        const double *rowp = tile + (size_t)wc * KS + 2 * j;
+#pragma unroll
+        for (int i = 0; i < HALF; i++) {
+          double2 v = *reinterpret_cast<const double2 *>(rowp + 2 * L * i);
+          e[u][2 * i] = v.x;
+          e[u][2 * i + 1] = v.y;
+        }
+        cw[u] = valid[u] ? cnt_s[wc] : 0.0;
+      } else {  // long document: stream the row from L2
+        const int64_t z = b + wc;
+        const double *rowp = a.E + (size_t)(__ldg(a.term_id + z) - 1) * KS + 2 * j;
+#pragma unroll
+        for (int i = 0; i < HALF; i++) {
+          double2 v = __ldg(reinterpret_cast<const double2 *>(rowp + 2 * L * i));
+          e[u][2 * i] = v.x;
+          e[u][2 * i + 1] = v.y;
+        }
+        cw[u] = valid[u] ? (double)__ldg(a.count + z) : 0.0;
+      }
+    }
+    // norm_w = sum_k theta_k E_wk   (updatePhi's normalizeFactor, DocumentMapper.java:408-415)
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < KPL; i += 4) {
+        a0 = fma(th[i], e[u][i], a0);
+        if (i + 1 < KPL) a1 = fma(th[i + 1], e[u][i + 1], a1);
+        if (i + 2 < KPL) a2 = fma(th[i + 2], e[u][i + 2], a2);
+        if (i + 3 < KPL) a3 = fma(th[i + 3], e[u][i + 3], a3);
+      }
+      dot[u] = (a0 + a1) + (a2 + a3);
+    }
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) {
+#pragma unroll
+      for (int u = 0; u < U; u++) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], o);
+    }
+    bool bad[U];
+    double r[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      bad[u] = valid[u] && !(dot[u] >= MRLDA_NORM_TINY);
+      r[u] = (valid[u] && !bad[u]) ? cw[u] * rcp_fast(dot[u]) : 0.0;
+    }
+    // S_k += (n_w / norm_w) E_wk   (updateLogGamma fold, DocumentMapper.java:424-425)
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+#pragma unroll
+      for (int i = 0; i < KPL; i++) s[i] = fma(r[u], e[u][i], s[i]);
+    }
+
+    if (LAST) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const int w = rbu[u] * RPB + g;
+        const int term = __ldg(a.term_id + b + (w < n ? w : n - 1));
+        if (valid[u] && !bad[u] && j == 0)
+          lik = fma(cw[u], log(dot[u]) + __ldg(a.rowmax + term - 1), lik);
+        if (a.learning && valid[u] && !bad[u]) {
+          double *srow = a.stats + (size_t)(term - 1) * K;
+#pragma unroll
+          for (int i = 0; i < KPL; i++) {
+            int col = 2 * (j + L * (i >> 1)) + (i & 1);
+            if (col < K) atomicAdd(srow + col, r[u] * th[i] * e[u][i]);
+          }
+        }
+      }
+    }
+
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      unsigned badmask = __ballot_sync(0xffffffffu, bad[u]);
+      while (badmask) {  // exact log-space redo of the rows whose norm underflowed (rare)
+        const int gi = (__ffs(badmask) - 1) / L;
+        badmask &= ~((L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (gi * L));
+        const int64_t z = b + rbu[u] * RPB + gi;
+        const int term = __ldg(a.term_id + z);
+        const double nw_ = (double)__ldg(a.count + z);
+        const double *lb = a.logbeta + (size_t)(term - 1) * K;
+        double mx = -INFINITY;
+        for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gam_s[k]));
+        mx = warp_max(mx);
+        double sum = 0.0;
+        for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gam_s[k]) - mx);
+        sum = warp_sum(sum);
+        const double lsum = log(sum);
+        for (int k = lane; k < K; k += 32) {
+          double lphi = lb[k] + digamma_fast(gam_s[k]) - mx - lsum;
+          double c = nw_ * exp(lphi);
+          if (c > 0.0) {
+            atomicAdd(gextra_s + k, c);
+            if (LAST) {
+              lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
+              if (a.learning) atomicAdd(a.stats + (size_t)(term - 1) * K + k, c);
+            }
+          }
+        }
+        if (lane == 0) atomicAdd(a.slow_rows, 1);
+      }
+    }
+  }
+}
+
 template <int L, int KPL>
 __global__ void __launch_bounds__(EstepShape<L, KPL>::MAX_THREADS, 1)
 estep_kernel(const EstepArgs a) {
   using S = EstepShape<L, KPL>;
-  constexpr int RPB = S::RPB, KS = S::KS, HALF = S::HALF;
+  constexpr int RPB = S::RPB, KS = S::KS, HALF = S::HALF, UNROLL = S::UNROLL;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, T = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, NW = T >> 5;
@@ -210,93 +344,12 @@ estep_kernel(const EstepArgs a) {
         s[2 * i + 1] = 0.0;
       }
 
-      for (int rb = warp; rb < nblocks; rb += NW) {
-        const int w = rb * RPB + g;
-        const bool valid = w < n;
-        const int wc = valid ? w : n - 1;
-        double e[KPL];
-        double cw;
-        if (rb * RPB < cap) {  // warp-uniform: rows resident in the tile
-          const double *rowp = tile + (size_t)wc * KS + 2 * j;
-#pragma unroll
-          for (int i = 0; i < HALF; i++) {
-            double2 v = *reinterpret_cast<const double2 *>(rowp + 2 * L * i);
-            e[2 * i] = v.x;
-            e[2 * i + 1] = v.y;
-          }
-          cw = valid ? cnt_s[wc] : 0.0;
-        } else {  // long document: stream the row from L2
-          const int64_t z = b + wc;
-          const double *rowp = a.E + (size_t)(__ldg(a.term_id + z) - 1) * KS + 2 * j;
-#pragma unroll
-          for (int i = 0; i < HALF; i++) {
-            double2 v = __ldg(reinterpret_cast<const double2 *>(rowp + 2 * L * i));
-            e[2 * i] = v.x;
-            e[2 * i + 1] = v.y;
-          }
-          cw = valid ? (double)__ldg(a.count + z) : 0.0;
-        }
-        // norm_w = sum_k theta_k E_wk   (updatePhi's normalizeFactor, DocumentMapper.java:408-415)
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-        for (int i = 0; i < KPL; i += 4) {
-          a0 = fma(th[i], e[i], a0);
-          if (i + 1 < KPL) a1 = fma(th[i + 1], e[i + 1], a1);
-          if (i + 2 < KPL) a2 = fma(th[i + 2], e[i + 2], a2);
-          if (i + 3 < KPL) a3 = fma(th[i + 3], e[i + 3], a3);
-        }
-        double dot = (a0 + a1) + (a2 + a3);
-#pragma unroll
-        for (int o = 1; o < L; o <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-
-        const bool bad = valid && !(dot >= MRLDA_NORM_TINY);
-        double r = (valid && !bad) ? cw * rcp_fast(dot) : 0.0;
-        // S_k += (n_w / norm_w) E_wk   (updateLogGamma fold, DocumentMapper.java:424-425)
-#pragma unroll
-        for (int i = 0; i < KPL; i++) s[i] = fma(r, e[i], s[i]);
-
-        if (last) {
-          const int term = __ldg(a.term_id + b + wc);
-          if (valid && !bad && j == 0) lik = fma(cw, log(dot) + __ldg(a.rowmax + term - 1), lik);
-          if (a.learning && valid && !bad) {
-            double *srow = a.stats + (size_t)(term - 1) * K;
-#pragma unroll
-            for (int i = 0; i < KPL; i++) {
-              int col = 2 * (j + L * (i >> 1)) + (i & 1);
-              if (col < K) atomicAdd(srow + col, r * th[i] * e[i]);
-            }
-          }
-        }
-
-        unsigned badmask = __ballot_sync(0xffffffffu, bad);
-        while (badmask) {  // exact log-space redo of the rows whose norm underflowed (rare)
-          const int gi = (__ffs(badmask) - 1) / L;
-          badmask &= ~((L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (gi * L));
-          const int64_t z = b + rb * RPB + gi;
-          const int term = __ldg(a.term_id + z);
-          const double nw_ = (double)__ldg(a.count + z);
-          const double *lb = a.logbeta + (size_t)(term - 1) * K;
-          double mx = -INFINITY;
-          for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gam_s[k]));
-          mx = warp_max(mx);
-          double sum = 0.0;
-          for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gam_s[k]) - mx);
-          sum = warp_sum(sum);
-          const double lsum = log(sum);
-          for (int k = lane; k < K; k += 32) {
-            double lphi = lb[k] + digamma_fast(gam_s[k]) - mx - lsum;
-            double c = nw_ * exp(lphi);
-            if (c > 0.0) {
-              atomicAdd(gextra_s + k, c);
-              if (last) {
-                lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
-                if (a.learning) atomicAdd(a.stats + (size_t)(term - 1) * K + k, c);
-              }
-            }
-          }
-          if (lane == 0) atomicAdd(a.slow_rows, 1);
-        }
-      }
+      if (!last)
+        sweep_rows<L, KPL, UNROLL, false>(a, tile, cnt_s, gam_s, gextra_s, th, s, lik, b, n, cap, nblocks,
+                                          warp, NW, lane);
+      else
+        sweep_rows<L, KPL, 1, true>(a, tile, cnt_s, gam_s, gextra_s, th, s, lik, b, n, cap, nblocks,
+                                    warp, NW, lane);
 
       // ---- S partials: reduce over the row groups of the warp, publish per warp ----
       {
