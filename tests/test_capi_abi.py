@@ -1,0 +1,55 @@
+"""The C-ABI library loads and exports every symbol include/mrlda_b200.h declares.
+No compute calls: this runs without a GPU."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mrlda_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrlda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(capi):
+    lib = capi.load()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/mrlda_b200.h but not exported"
+    assert sorted(capi.EXPORTS) == names
+
+
+def test_struct_layouts_match_header(capi):
+    assert ctypes.sizeof(capi.MrldaConfig) == 56
+    assert ctypes.sizeof(capi.MrldaIterResult) == 88
+    cfg = capi.default_config()
+    assert (cfg.sweep_cap, cfg.learning, cfg.world_size, cfg.update_alpha) == (100, 1, 1, 1)
+    assert cfg.eta == 1e-12 and cfg.random_start == 0 and cfg.symmetric_alpha == 0
+    assert capi.load().mrlda_version().decode().startswith("mrlda_b200")
+
+
+def test_no_cpu_fallback(capi):
+    """Without a GPU mrlda_create must fail loudly (MRLDA_ECUDA), never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    try:
+        capi.Context(4, 10)
+    except capi.MrldaError as e:
+        assert e.code == -2 and "no CPU fallback" in str(e)
+    else:
+        raise AssertionError("mrlda_create succeeded without a CUDA device")
+
+
+def test_product_package_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing under mrlda_b200/ may import, load or link it."""
+    pkg = os.path.join(ROOT, "mrlda_b200")
+    bad = re.compile(r"import\s+oracle|from\s+oracle|libmrlda_oracle|mrlda_oracle_[a-z]|oracle/_ref")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not bad.search(text), f"{f} uses the oracle"
