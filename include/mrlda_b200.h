@@ -160,6 +160,10 @@ int mrlda_comm_init(mrlda_ctx *ctx, const uint8_t id[MRLDA_NCCL_ID_BYTES]);
  * reports: at the reference's fixed 99 sweeps the E-step is FP64-pipe bound. */
 int mrlda_measure_fp64_peak(mrlda_ctx *ctx, double *tflops);
 
+/* Profiling aid: per-phase cycle counters of the register-stationary E-step kernel, accumulated by
+ * one thread; all zero unless the library was built with -DMRLDA_PHASE_TIMING.  Reading resets. */
+int mrlda_debug_phase_cycles(mrlda_ctx *ctx, int64_t out[16]);
+
 /* Number of this library's kernels launched on the context since creation. */
 int64_t mrlda_kernel_launches(const mrlda_ctx *ctx);
 /* Library/build description, e.g. "mrlda_b200 0.1 sm_100a". */

@@ -19,7 +19,7 @@ EXPORTS = [
     "mrlda_get_beta", "mrlda_set_logbeta", "mrlda_get_logbeta", "mrlda_init_beta_random",
     "mrlda_iterate", "mrlda_e_step", "mrlda_m_step", "mrlda_get_gamma", "mrlda_get_alpha_ss",
     "mrlda_get_stats", "mrlda_update_vector_alpha", "mrlda_update_scalar_alpha",
-    "mrlda_eval_special", "mrlda_measure_fp64_peak", "mrlda_nccl_unique_id", "mrlda_comm_init", "mrlda_kernel_launches",
+    "mrlda_eval_special", "mrlda_measure_fp64_peak", "mrlda_debug_phase_cycles", "mrlda_nccl_unique_id", "mrlda_comm_init", "mrlda_kernel_launches",
     "mrlda_version",
 ]
 
@@ -96,6 +96,7 @@ def load():
     L.mrlda_update_scalar_alpha.argtypes = [_ctxp, C.c_int32, C.c_int32, C.c_double, C.c_double, _dp]
     L.mrlda_eval_special.argtypes = [_ctxp, C.c_int32, C.c_int64, _dp, _dp]
     L.mrlda_measure_fp64_peak.argtypes = [_ctxp, _dp]
+    L.mrlda_debug_phase_cycles.argtypes = [_ctxp, _lp]
     L.mrlda_nccl_unique_id.argtypes = [_bp]
     L.mrlda_comm_init.argtypes = [_ctxp, _bp]
     L.mrlda_kernel_launches.argtypes = [_ctxp]
@@ -281,6 +282,11 @@ class Context:
         out = C.c_double(0)
         self._ck(load().mrlda_measure_fp64_peak(self._h, C.byref(out)))
         return out.value
+
+    def debug_phase_cycles(self):
+        out = np.zeros(16, dtype=np.int64)
+        self._ck(load().mrlda_debug_phase_cycles(self._h, out.ctypes.data_as(_lp)))
+        return out
 
     def kernel_launches(self):
         return int(load().mrlda_kernel_launches(self._h))

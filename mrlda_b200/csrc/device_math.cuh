@@ -59,26 +59,55 @@ __device__ __forceinline__ double rcp_fast(double x) {
   return y;
 }
 
+// exp(u) for u <= ~1 with a short dependency chain: Cody-Waite reduction, degree-12 Taylor
+// polynomial in Estrin form (|r| <= ln2/2: truncation 2e-16), exponent built by integer add.
+// Returns 0 for u < -708 (the result would be subnormal; callers treat such weights as 0).
+__device__ __forceinline__ double exp_short(double u) {
+  const double magic = 6755399441055744.0;  // 1.5 * 2^52: rint() in the low mantissa bits
+  double t = fma(u, 1.4426950408889634074, magic);
+  const int n = __double2loint(t);
+  const double nf = t - magic;
+  double r = fma(nf, -6.93147180369123816490e-01, u);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double a0 = 1.0 + r;
+  const double a1 = fma(r, 1.0 / 6.0, 0.5);
+  const double a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0);
+  const double a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
+  const double a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0);
+  const double a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0);
+  const double b0 = fma(a1, r2, a0);
+  const double b1 = fma(a3, r2, a2);
+  const double b2 = fma(a5, r2, a4);
+  const double d0 = fma(b1, r4, b0);
+  const double d1 = fma(1.0 / 479001600.0, r4, b2);
+  const double p = fma(d1, r8, d0);
+  const double scale = __hiloint2double((n + 1023) << 20, 0);
+  return u < -708.0 ? 0.0 : p * scale;
+}
+
 // The same digamma series restructured for the E-step's inner fixed point
 // (DocumentMapper.java:208-211 evaluates it K times per sweep, 99 sweeps per document):
 //   psi(x) = P(1/x6^2) + log(x6) - 0.5/x6 - sum_{j=0..5} 1/(t+j),  x6 = x+6, t = x6-6
 // with the six reciprocals folded into one rational Q'(t)/Q(t), Q(t) = t(t+1)...(t+5), and a single
-// reciprocal 1/(x6*Q).  t keeps the reference's (x+6)-6 rounding.  Returns u = psi(x) - log(x6) and
-// x6, so that exp(psi(x)) = x6 * exp(u) needs no logarithm.  |difference to the literal form| is a
-// few ulp of the largest term (no cancellation: all Q/Q' coefficients are positive).
+// reciprocal 1/(x6*Q).  With y = t^2 + 5t:  Q = y (y+4) (y+6),  Q' = (2t+5)(3y^2 + 20y + 24), which
+// keeps the dependency chain short.  t keeps the reference's (x+6)-6 rounding.  Returns
+// u = psi(x) - log(x6) and x6, so that exp(psi(x)) = x6 * exp(u) needs no logarithm.  The difference
+// to the literal form is a few ulp of the largest term (no cancellation: every factor is positive).
 __device__ __forceinline__ double digamma_minus_log(double x, double &x6_out) {
-  double x6 = x + 6.0;
-  double t = x6 - 6.0;
-  double q = fma(fma(fma(fma(fma(t, 1.0, 15.0), t, 85.0), t, 225.0), t, 274.0), t, 120.0) * t;
-  double dq = fma(fma(fma(fma(fma(6.0, t, 75.0), t, 340.0), t, 675.0), t, 548.0), t, 120.0);
-  double inv = rcp_fast(x6 * q);   // 1/(x6*Q)
-  double rx6 = q * inv;            // 1/x6
-  double ratio = dq * (x6 * inv);  // Q'/Q
+  const double x6 = x + 6.0;
+  const double t = x6 - 6.0;
+  const double y = fma(t, t, 5.0 * t);
+  const double q = y * ((y + 4.0) * (y + 6.0));
+  const double dq = fma(2.0, t, 5.0) * fma(fma(3.0, y, 20.0), y, 24.0);
+  const double inv = rcp_fast(x6 * q);  // 1/(x6*Q)
+  const double rx6 = q * inv;           // 1/x6
+  const double ratio = (dq * x6) * inv; // Q'/Q
   double p = rx6 * rx6;
   p = fma(fma(fma(0.004166666666667, p, -0.003968253986254), p, 0.008333333333333), p,
           -0.083333333333333) * p;
   x6_out = x6;
-  return p - 0.5 * rx6 - ratio;
+  return fma(-0.5, rx6, p - ratio);
 }
 
 // psi(x) by the restructured series.
@@ -92,7 +121,7 @@ __device__ __forceinline__ double digamma_fast(double x) {
 __device__ __forceinline__ double exp_digamma(double x) {
   double x6;
   double u = digamma_minus_log(x, x6);
-  return x6 * exp(u);
+  return x6 * exp_short(u);
 }
 
 // LogMath.add without a drop threshold (see oracle/mrlda_oracle.c header for the pinning status).

@@ -1,0 +1,505 @@
+// estep2_kernel.cuh — K1, register-stationary variant: the E-step hot kernel for documents whose
+// n_d x K tile fits on one SM (registers + shared memory).
+//
+// Same arithmetic as estep_kernel.cuh (linear-space fixed point, 99 sweeps, exact log-space redo of
+// underflowing rows; reference: DocumentMapper.java:175-350, updatePhi :402-429); different mapping.
+//
+//   * Topics are split across the NW warps of the CTA: warp w owns the CPW columns
+//     [w*CPW, (w+1)*CPW).  Rows (distinct terms of the document) are split across lanes: lane l owns
+//     rows l, l+32, l+64, ... ("slots").  Thread (w,l) therefore owns the E elements
+//     (row 32q+l, columns of warp w) for every slot q, and nobody else ever touches them.
+//   * The first RREG slots live in REGISTERS for all 99 sweeps (the register file, 256 KB, is the
+//     largest on-chip memory of the SM); further slots live in a thread-private region of shared
+//     memory.  The hot loop reads no shared E data for documents of up to 32*RREG rows.
+//   * Per sweep: (1) the lane that owns a column computes theta_c = exp(digamma(gamma_c)) and the
+//     warp broadcasts its CPW thetas; (2) every thread forms the partial dot products of its rows
+//     over its warp's columns and publishes them; CTA barrier; (3a) one thread per row sums the NW
+//     partials (norm_w) and publishes r_w = n_w / norm_w; CTA barrier; (3b) every thread
+//     accumulates S_c += r_w E_wc over its rows; (4) the per-lane S vectors of a warp are
+//     transposed through shared memory (or reduce-scattered in registers) so that S_c lands in the
+//     lane that owns column c, which updates gamma_c.  gamma, alpha and the alpha sufficient
+//     statistics stay in the owner lane's registers.
+//   * WPS = warps per SM the variant is compiled for: 8 (255 registers per thread, most of the tile
+//     in registers) or 16 (128 registers per thread, more of the tile in shared memory, twice the
+//     warps to hide the FP64 / shared-memory latencies of the serial phases).
+//   * Work is perfectly balanced across warps (every warp walks all rows); the only idle lanes are
+//     those of the last, partially filled slot.
+#pragma once
+#include "estep_kernel.cuh"
+
+#ifdef MRLDA_PHASE_TIMING
+#define MRLDA_TICK(i) tm[i] = clock64()
+#else
+#define MRLDA_TICK(i)
+#endif
+
+namespace mrlda {
+
+template <int NW, int CPW, int RREG, int WPS>
+struct Estep2Shape {
+  static constexpr int THREADS = NW * 32;
+  static constexpr int CTAS_PER_SM = WPS / NW;
+  static constexpr int KS = NW * CPW;
+  static constexpr int HALF = CPW / 2;
+  static_assert(CPW % 2 == 0 && CPW <= 32, "CPW must be even and at most 32");
+  static_assert(NW == 1 || NW == 2 || NW == 4 || NW == 8 || NW == 16, "NW in {1,2,4,8,16}");
+  static_assert((WPS == 8 || WPS == 16) && NW <= WPS, "WPS in {8,16}");
+};
+
+// register-resident slots: what fits in 255 registers next to the working set (theta or S: 2*CPW
+// registers, partial sums, addresses) without spilling E into local memory (-Xptxas -v)
+__host__ __device__ constexpr int estep2_rreg(int cpw, int wps = 8) {
+  int r = wps == 8 ? (255 - 75 - 2 * cpw) / (2 * cpw) : (128 - 44 - 2 * cpw) / (2 * cpw);
+  return r < 1 ? 1 : (r > 8 ? 8 : r);
+}
+
+// shared memory bytes: rsm slots of thread-private E, double-buffered partials, small arrays
+template <int NW, int CPW>
+__host__ __device__ constexpr size_t estep2_smem_bytes(int rsm, int cap_rows) {
+  return sizeof(double) * ((size_t)rsm * NW * 32 * CPW   // E slots
+                           + 2 * (size_t)NW * cap_rows   // partial dots, two buffers
+                           + 2 * (size_t)cap_rows        // counts, r
+                           + 3 * (size_t)NW * CPW        // theta, gamma, gextra
+                           + 96);                        // reductions + doc meta
+}
+
+template <int NW, int CPW, int RREG, bool LAST>
+__device__ __forceinline__ void estep2_sweep(
+    const EstepArgs &a, double (&e)[RREG][CPW], const double *es, double *part, const double *cnt_s,
+    double *r_s, int *flag_s, const double *theta_w, double (&s)[CPW], double &lik,
+    unsigned &badbits, const int64_t b, const int n, const int nslots, const int cap_rows,
+    const int warp, const int lane, long long *tm) {
+  (void)tm;
+  constexpr int HALF = CPW / 2;
+  const int K = a.K;
+  // (2) partial dot products of my rows over my warp's columns.  Register slots are processed
+  // unconditionally (an unused slot holds zeros) so that the chains of different slots interleave;
+  // theta is read just in time (warp-wide broadcast loads) to keep registers for the tile.
+  double *pw = part + (size_t)warp * cap_rows + lane;
+  {
+    double acc[RREG][2];
+#pragma unroll
+    for (int q = 0; q < RREG; q++) acc[q][0] = acc[q][1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+      const double2 tv = *reinterpret_cast<const double2 *>(theta_w + 2 * i);
+#pragma unroll
+      for (int q = 0; q < RREG; q++) {
+        acc[q][0] = fma(tv.x, e[q][2 * i], acc[q][0]);
+        acc[q][1] = fma(tv.y, e[q][2 * i + 1], acc[q][1]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < RREG; q++) pw[32 * q] = acc[q][0] + acc[q][1];
+  }
+  if (nslots > RREG) {  // slots that live in shared memory: theta held in registers for all of them
+    double th[CPW];
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+      const double2 tv = *reinterpret_cast<const double2 *>(theta_w + 2 * i);
+      th[2 * i] = tv.x;
+      th[2 * i + 1] = tv.y;
+    }
+    for (int q = RREG; q < nslots; q++) {
+      const double2 *src = reinterpret_cast<const double2 *>(es) +
+                           ((size_t)((q - RREG) * NW + warp) * HALF) * 32 + lane;
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int i = 0; i < HALF; i++) {
+        const double2 v = src[(size_t)i * 32];
+        a0 = fma(th[2 * i], v.x, a0);
+        a1 = fma(th[2 * i + 1], v.y, a1);
+      }
+      pw[32 * q] = a0 + a1;
+    }
+  }
+  MRLDA_TICK(2);
+  __syncthreads();  // B1: partial dots published
+  MRLDA_TICK(3);
+
+  // (3a) one thread per row: norm_w = sum of the NW partials, r_w = n_w / norm_w; a row whose norm
+  // underflowed is flagged with r = -1 and redone exactly in log space by the caller
+  {
+    const int nrows = 32 * (nslots > RREG ? nslots : RREG);
+    for (int row = warp * 32 + lane; row < nrows; row += NW * 32) {
+      const double *pp = part + row;
+      double n0 = pp[0], n1 = 0.0, n2 = 0.0, n3 = 0.0;
+#pragma unroll
+      for (int w2 = 1; w2 < NW; w2++) {
+        const double v = pp[(size_t)w2 * cap_rows];
+        if ((w2 & 3) == 0) n0 += v;
+        else if ((w2 & 3) == 1) n1 += v;
+        else if ((w2 & 3) == 2) n2 += v;
+        else n3 += v;
+      }
+      const double norm = (n0 + n1) + (n2 + n3);
+      const bool valid = row < n;
+      const bool bad = valid && !(norm >= MRLDA_NORM_TINY);
+      const bool ok = valid && !bad;
+      const double cn = cnt_s[row];
+      r_s[row] = bad ? -1.0 : (ok ? cn : 0.0) * rcp_fast(ok ? norm : 1.0);
+      if (bad) *flag_s = 1;
+      if (LAST && ok)  // likelihoodPhi, first part (DocumentMapper.java:421 summed over topics)
+        lik = fma(cn, log(norm) + __ldg(a.rowmax + __ldg(a.term_id + b + row) - 1), lik);
+    }
+  }
+  MRLDA_TICK(4);
+  __syncthreads();  // B2: r published
+  MRLDA_TICK(5);
+
+  // (3b) S_c += r_w E_wc over my rows
+#pragma unroll
+  for (int c = 0; c < CPW; c++) s[c] = 0.0;
+  badbits = 0;
+  auto scatter = [&](int q, double r, const double *erow) {
+    // statistics scatter of the last sweep: n_w phi_wk = r_w theta_k E_wk (DocumentMapper.java:315-329)
+    if (!(r > 0.0) || !a.learning) return;
+    const int term = __ldg(a.term_id + b + 32 * q + lane);
+    double *srow = a.stats + (size_t)(term - 1) * K + warp * CPW;
+#pragma unroll
+    for (int c = 0; c < CPW; c++)
+      if (warp * CPW + c < K) atomicAdd(srow + c, r * theta_w[c] * erow[c]);
+  };
+  {
+    double r[RREG];
+#pragma unroll
+    for (int q = 0; q < RREG; q++) {
+      r[q] = r_s[32 * q + lane];
+      if (r[q] < 0.0) {
+        badbits |= 1u << q;
+        r[q] = 0.0;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CPW; c++) {
+#pragma unroll
+      for (int q = 0; q < RREG; q++) s[c] = fma(r[q], e[q][c], s[c]);
+    }
+    if (LAST) {
+#pragma unroll
+      for (int q = 0; q < RREG; q++) scatter(q, r[q], e[q]);
+    }
+  }
+  for (int q = RREG; q < nslots; q++) {
+    double r = r_s[32 * q + lane];
+    if (r < 0.0) {
+      badbits |= 1u << q;
+      r = 0.0;
+    }
+    const double2 *src = reinterpret_cast<const double2 *>(es) +
+                         ((size_t)((q - RREG) * NW + warp) * HALF) * 32 + lane;
+    double tmp[CPW];
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+      double2 v = src[(size_t)i * 32];
+      tmp[2 * i] = v.x;
+      tmp[2 * i + 1] = v.y;
+      s[2 * i] = fma(r, v.x, s[2 * i]);
+      s[2 * i + 1] = fma(r, v.y, s[2 * i + 1]);
+    }
+    if (LAST) scatter(q, r, tmp);
+  }
+}
+
+template <int NW, int CPW, int RREG, int WPS>
+__global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepArgs a) {
+  constexpr int HALF = CPW / 2, KS = NW * CPW;
+  extern __shared__ __align__(16) double smem[];
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int K = a.K;
+  const int cap_rows = a.cap_rows;          // 32 * (RREG + rsm)
+  const int rsm = cap_rows / 32 - RREG;
+
+  double *es = smem;                                        // rsm x NW x HALF x 32 double2
+  double *part_s = es + (size_t)rsm * NW * 32 * CPW;        // 2 x NW x cap_rows
+  double *cnt_s = part_s + 2 * (size_t)NW * cap_rows;       // cap_rows
+  double *r_s = cnt_s + cap_rows;                           // cap_rows
+  double *theta_s = r_s + cap_rows;                         // KS
+  double *gam_s = theta_s + KS;                             // KS
+  double *gextra_s = gam_s + KS;                            // KS
+  double *red_s = gextra_s + KS;                            // 96: 3 x 16 sums, then doc meta
+  int *meta_s = reinterpret_cast<int *>(red_s + 64);        // [0] document, [1] slow-path flag
+
+  // Lane c owns column c of its warp (gamma_c, alpha_c, theta_c live in its registers).  The
+  // register reduce-scatter leaves column rs_col in this lane; rs_src is the lane that ends up
+  // with the column this lane owns.
+  const int mycol = lane < CPW ? lane : -1;
+  int rs_src = 0;
+  {
+    double dummy[CPW];
+#pragma unroll
+    for (int c = 0; c < CPW; c++) dummy[c] = 0.0;
+    int base = 0, cnt = CPW;
+    reduce_scatter<CPW, 16, 1, CPW>(dummy, lane, base, cnt);
+    const int rs_col = cnt > 0 ? base : -1;
+    for (int l2 = 0; l2 < 32; l2++) {
+      int c2 = __shfl_sync(0xffffffffu, rs_col, l2);
+      if (c2 == lane) rs_src = l2;
+    }
+  }
+  const int col = warp * CPW + mycol;
+  const bool owner = mycol >= 0 && col < K;
+  const double alpha_c = owner ? a.alpha[col] : 1.0;
+  double ss_acc = 0.0;  // my column's alpha sufficient statistic over all my documents
+  const double lik_alpha = *a.lik_alpha;
+  for (int k = tid; k < KS; k += NW * 32) {
+    theta_s[k] = 0.0;
+    gextra_s[k] = 0.0;
+    gam_s[k] = 1.0;
+  }
+  if (tid == 0) meta_s[1] = 0;
+  double *theta_w = theta_s + warp * CPW;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) meta_s[0] = a.doc_begin + atomicAdd(a.work_counter, 1);
+    __syncthreads();
+    const int qi = meta_s[0];
+    if (qi >= a.doc_end) break;
+    const int d = a.doc_order[qi];
+    const int64_t b = a.row_ptr[d];
+    const int n = (int)(a.row_ptr[d + 1] - b);
+    if (n <= 0) continue;  // DocumentMapper.java:197-201: null content, nothing is updated
+    const int nslots = (n + 31) >> 5;
+
+    // ---- load my elements: E rows of my slots, my warp's column slice (compulsory traffic) ----
+    double e[RREG][CPW];
+#pragma unroll
+    for (int q = 0; q < RREG; q++) {
+      const int row = 32 * q + lane;
+      if (row < n) {
+        const double2 *src = reinterpret_cast<const double2 *>(
+            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+#pragma unroll
+        for (int i = 0; i < HALF; i++) {
+          double2 v = __ldg(src + i);
+          e[q][2 * i] = v.x;
+          e[q][2 * i + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < CPW; c++) e[q][c] = 0.0;
+      }
+    }
+    for (int q = RREG; q < nslots; q++) {
+      const int row = 32 * q + lane;
+      double2 *dst = reinterpret_cast<double2 *>(es) + ((size_t)((q - RREG) * NW + warp) * HALF) * 32 + lane;
+      if (row < n) {
+        const double2 *src = reinterpret_cast<const double2 *>(
+            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+#pragma unroll
+        for (int i = 0; i < HALF; i++) dst[(size_t)i * 32] = __ldg(src + i);
+      } else {
+#pragma unroll
+        for (int i = 0; i < HALF; i++) dst[(size_t)i * 32] = make_double2(0.0, 0.0);
+      }
+    }
+    {
+      const int fill = 32 * (nslots > RREG ? nslots : RREG);  // register slots are always walked
+      for (int r = tid; r < fill; r += NW * 32) cnt_s[r] = r < n ? (double)a.count[b + r] : 0.0;
+    }
+    // gamma start (DocumentMapper.java:184-193)
+    double gam = 1.0;
+    if (owner) {
+      if (a.use_stored_gamma)
+        gam = a.gamma[(size_t)d * K + col];
+      else
+        gam = alpha_c + (double)((float)a.doc_tokens[d] / (float)K);
+    }
+    __syncthreads();
+
+    double lik = 0.0, theta_c = 0.0;
+    double s[CPW];
+    unsigned badbits = 0;
+    for (int sweep = 0; sweep < a.sweeps; sweep++) {
+      const bool last = (sweep == a.sweeps - 1);
+      long long tm[8];
+      (void)tm;
+      MRLDA_TICK(0);
+      // (1) theta_c = exp(digamma(gamma_c)) in the owner lane, broadcast within the warp
+      theta_c = owner ? exp_digamma(gam) : 0.0;
+      if (mycol >= 0) theta_w[mycol] = theta_c;
+      __syncwarp();
+      MRLDA_TICK(1);
+      double *part = part_s + (size_t)(sweep & 1) * NW * cap_rows;
+      if (!last)
+        estep2_sweep<NW, CPW, RREG, false>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
+                                           badbits, b, n, nslots, cap_rows, warp, lane, tm);
+      else
+        estep2_sweep<NW, CPW, RREG, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
+                                          badbits, b, n, nslots, cap_rows, warp, lane, tm);
+      MRLDA_TICK(6);
+      // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
+      // document leaves it free, else reduce-scatter in registers
+      double S_c;
+      if (a.rs_smem && nslots < RREG + rsm) {
+        double *scr = es + ((size_t)(rsm - 1) * NW + warp) * 32 * CPW;
+#pragma unroll
+        for (int c = 0; c < CPW; c++) scr[c * 32 + lane] = s[c];
+        __syncwarp();
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (lane < CPW) {
+          const double *colp = scr + lane * 32;
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            double2 v = *reinterpret_cast<const double2 *>(colp + 2 * ((i + lane) & 15));
+            double2 u = *reinterpret_cast<const double2 *>(colp + 2 * ((i + 1 + lane) & 15));
+            a0 += v.x;
+            a1 += v.y;
+            a2 += u.x;
+            a3 += u.y;
+          }
+        }
+        S_c = (a0 + a1) + (a2 + a3);
+      } else {
+        int base = 0, cnt = CPW;
+        reduce_scatter<CPW, 16, 1, CPW>(s, lane, base, cnt);
+        S_c = __shfl_sync(0xffffffffu, s[0], rs_src);
+      }
+      MRLDA_TICK(7);
+#ifdef MRLDA_PHASE_TIMING
+      if (blockIdx.x == 0 && tid == 0 && !last) {
+        for (int i = 0; i < 7; i++) a.phase_cycles[i] += tm[i + 1] - tm[i];
+        a.phase_cycles[7] += 1;
+        a.phase_cycles[8] += nslots;
+      }
+#endif
+      // rows whose norm underflowed: exact log-space redo by warp 0 (CTA-uniform branch: every
+      // warp computed the same norms)
+      const bool anybad = meta_s[1] != 0;  // written before B2 by the row threads: CTA-uniform
+      if (anybad) {
+        if (owner) gam_s[col] = gam;
+        __syncthreads();
+        if (tid == 0) meta_s[1] = 0;
+        if (warp == 0) {
+          for (int q = 0; q < nslots; q++) {
+            unsigned m = __ballot_sync(0xffffffffu, (badbits >> q) & 1u);
+            while (m) {
+              const int l2 = __ffs(m) - 1;
+              m &= m - 1;
+              const int64_t z = b + 32 * q + l2;
+              const int term = __ldg(a.term_id + z);
+              const double nw_ = (double)__ldg(a.count + z);
+              const double *lb = a.logbeta + (size_t)(term - 1) * K;
+              double mx = -INFINITY;
+              for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gam_s[k]));
+              mx = warp_max(mx);
+              double sum = 0.0;
+              for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gam_s[k]) - mx);
+              sum = warp_sum(sum);
+              const double lsum = log(sum);
+              for (int k = lane; k < K; k += 32) {
+                double lphi = lb[k] + digamma_fast(gam_s[k]) - mx - lsum;
+                double c = nw_ * exp(lphi);
+                if (c > 0.0) {
+                  gextra_s[k] += c;  // one warp, distinct k per lane: no race
+                  if (last) {
+                    lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
+                    if (a.learning) atomicAdd(a.stats + (size_t)(term - 1) * K + k, c);
+                  }
+                }
+              }
+              if (lane == 0) atomicAdd(a.slow_rows, 1);
+            }
+          }
+        }
+        __syncthreads();
+      }
+      if (!last) {
+        if (owner) {
+          double gnew = fma(theta_c, S_c, alpha_c);  // DocumentMapper.java:232-234
+          if (anybad) {
+            gnew += gextra_s[col];
+            gextra_s[col] = 0.0;
+          }
+          gam = gnew;
+        }
+      } else {
+        // ---- document epilogue (DocumentMapper.java:244-259,342-346) ----
+        double g_new = 1.0, lg = 0.0;
+        if (owner) {
+          const double add = theta_c * S_c;
+          g_new = alpha_c + add;
+          if (anybad) {
+            g_new += gextra_s[col];
+            gextra_s[col] = 0.0;
+          }
+          if (add != 0.0) lik -= digamma_fast(gam) * add;
+          lg = lgamma(g_new);
+          a.gamma[(size_t)d * K + col] = g_new;
+        }
+        double sg = warp_sum(owner ? g_new : 0.0);
+        lg = warp_sum(lg);
+        lik = warp_sum(lik);
+        if (lane == 0) {
+          red_s[warp] = sg;
+          red_s[16 + warp] = lg;
+          red_s[32 + warp] = lik;
+        }
+        __syncthreads();
+        double tg = 0.0, tl = 0.0, tk = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; w2++) {
+          tg += red_s[w2];
+          tl += red_s[16 + w2];
+          tk += red_s[32 + w2];
+        }
+        __syncthreads();  // red_s is rewritten by the next document
+        if (owner) ss_acc += digamma_literal(g_new) - digamma_literal(tg);
+        if (tid == 0) {
+          double ll = lik_alpha + (tl - lgamma(tg)) + tk;
+          long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
+          atomicAdd(a.ll_counter, (unsigned long long)c);
+        }
+      }
+    }
+  }
+  // DocumentMapper.close (DocumentMapper.java:354-361)
+  if (owner && ss_acc != 0.0) atomicAdd(a.alpha_ss + col, ss_acc);
+}
+
+struct Estep2Variant {
+  int NW, CPW, RREG, WPS;
+  cudaError_t (*launch)(const EstepArgs &, int grid, int cap_rows, cudaStream_t);
+  size_t (*smem_bytes)(int rsm, int cap_rows);
+  cudaError_t (*prepare)(size_t smem);
+};
+
+template <int NW, int CPW>
+static size_t variant2_smem(int rsm, int cap_rows) {
+  return estep2_smem_bytes<NW, CPW>(rsm, cap_rows);
+}
+template <int NW, int CPW, int RREG, int WPS>
+static cudaError_t variant2_prepare(size_t smem) {
+  return cudaFuncSetAttribute(estep2_kernel<NW, CPW, RREG, WPS>,
+                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <int NW, int CPW, int RREG, int WPS>
+static cudaError_t variant2_launch(const EstepArgs &args, int grid, int cap_rows, cudaStream_t st) {
+  EstepArgs a = args;
+  a.cap_rows = cap_rows;
+  size_t smem = estep2_smem_bytes<NW, CPW>(cap_rows / 32 - RREG, cap_rows);
+  estep2_kernel<NW, CPW, RREG, WPS><<<grid, NW * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+#define MRLDA_VARIANT2R(NW_, CPW_, RREG_, WPS_)                                                  \
+  {                                                                                              \
+    NW_, CPW_, RREG_, WPS_, variant2_launch<NW_, CPW_, RREG_, WPS_>, variant2_smem<NW_, CPW_>,   \
+        variant2_prepare<NW_, CPW_, RREG_, WPS_>                                                 \
+  }
+#define MRLDA_VARIANT2(NW_, CPW_, WPS_) MRLDA_VARIANT2R(NW_, CPW_, estep2_rreg(CPW_, WPS_), WPS_)
+
+extern const Estep2Variant g_estep2_variants_W1[];
+extern const int g_estep2_variants_W1_n;
+extern const Estep2Variant g_estep2_variants_W2[];
+extern const int g_estep2_variants_W2_n;
+extern const Estep2Variant g_estep2_variants_W4[];
+extern const int g_estep2_variants_W4_n;
+extern const Estep2Variant g_estep2_variants_W8[];
+extern const int g_estep2_variants_W8_n;
+extern const Estep2Variant g_estep2_variants_W16[];
+extern const int g_estep2_variants_W16_n;
+
+}  // namespace mrlda

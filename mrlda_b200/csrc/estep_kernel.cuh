@@ -41,8 +41,10 @@ struct EstepArgs {
   const int32_t *doc_order;   // D, documents sorted by nnz descending
   const int32_t *doc_tokens;  // D, sum of counts
   int64_t n_docs;
+  int doc_begin, doc_end;     // range of doc_order this launch works on
   // model (device)
-  const double *E;        // V x KS, zero padded columns
+  const double *E;        // V x e_stride, columns >= K are zero
+  int e_stride;           // row stride of E in doubles (>= the kernel's KS, even)
   const double *rowmax;   // V
   const double *logbeta;  // V x K
   const double *alpha;    // K
@@ -54,11 +56,13 @@ struct EstepArgs {
   unsigned long long *ll_counter; // int64 two's complement accumulated with wrapping adds
   int *work_counter;
   int *slow_rows;
+  long long *phase_cycles;  // 16 counters, written only when built with -DMRLDA_PHASE_TIMING
   int K;
   int sweeps;
   int use_stored_gamma;
   int learning;
   int cap_rows;  // tile capacity in rows (multiple of RPB)
+  int rs_smem;   // register-stationary kernel: transpose S through shared memory (1) or shuffles (0)
 };
 
 #define MRLDA_NORM_TINY 1e-200
@@ -167,7 +171,7 @@ __device__ __forceinline__ void sweep_rows(const EstepArgs &a, const double *til
         cw[u] = valid[u] ? cnt_s[wc] : 0.0;
       } else {  // long document: stream the row from L2
         const int64_t z = b + wc;
-        const double *rowp = a.E + (size_t)(__ldg(a.term_id + z) - 1) * KS + 2 * j;
+        const double *rowp = a.E + (size_t)(__ldg(a.term_id + z) - 1) * a.e_stride + 2 * j;
 #pragma unroll
         for (int i = 0; i < HALF; i++) {
           double2 v = __ldg(reinterpret_cast<const double2 *>(rowp + 2 * L * i));
@@ -293,10 +297,10 @@ estep_kernel(const EstepArgs a) {
 
   for (;;) {
     __syncthreads();
-    if (tid == 0) meta_s[0] = atomicAdd(a.work_counter, 1);
+    if (tid == 0) meta_s[0] = a.doc_begin + atomicAdd(a.work_counter, 1);
     __syncthreads();
     const int qi = meta_s[0];
-    if (qi >= a.n_docs) break;
+    if (qi >= a.doc_end) break;
     const int d = a.doc_order[qi];
     const int64_t b = a.row_ptr[d];
     const int n = (int)(a.row_ptr[d + 1] - b);
@@ -310,7 +314,7 @@ estep_kernel(const EstepArgs a) {
       const int total = nt * UNITS;
       for (int u = tid; u < total; u += T) {
         int r = u / UNITS, c = u - r * UNITS;
-        const double *src = a.E + (size_t)(a.term_id[b + r] - 1) * KS + 2 * c;
+        const double *src = a.E + (size_t)(a.term_id[b + r] - 1) * a.e_stride + 2 * c;
         unsigned dst = (unsigned)__cvta_generic_to_shared(tile + (size_t)r * KS + 2 * c);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
       }

@@ -22,9 +22,13 @@
 #include <vector>
 
 #include "../../include/mrlda_b200.h"
-#include "estep_kernel.cuh"
+#include "estep2_kernel.cuh"
 
 using namespace mrlda;
+
+#ifndef MRLDA_DEFAULT_WPS
+#define MRLDA_DEFAULT_WPS 8
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // small device kernels
@@ -398,7 +402,10 @@ std::string g_global_error;
 struct mrlda_ctx {
   mrlda_config cfg;
   int K = 0, V = 0, KS = 0;
-  const EstepVariant *variant = nullptr;
+  const EstepVariant *variant = nullptr;    // general kernel (any document length)
+  const Estep2Variant *variant2 = nullptr;  // register-stationary kernel (documents that fit one SM)
+  int ES = 0;                               // row stride of E in doubles
+  std::vector<int32_t> h_nnz_sorted;        // nnz per document in doc_order (descending)
   int num_sms = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
@@ -426,6 +433,7 @@ struct mrlda_ctx {
   double *d_alpha_ss = nullptr;   // K
   long long *d_counters = nullptr; // [0] ll counter, [1] n_docs, [2] n_tokens, [3] slow rows
   int *d_work = nullptr;           // [0] work queue, [1] slow rows
+  long long *d_phase = nullptr;    // phase cycle counters (MRLDA_PHASE_TIMING builds)
   double *d_partial = nullptr, *d_colsum = nullptr, *d_alpha_work = nullptr;
   int nslabs = 0, slab = 0;
   int64_t total_docs = 0, total_tokens = 0, terms_seen = 0;
@@ -474,6 +482,40 @@ static const EstepVariant *select_variant(int K) {
   return best;
 }
 
+static const Estep2Variant *select_variant2(int K) {
+  const Estep2Variant *tabs[] = {g_estep2_variants_W1, g_estep2_variants_W2, g_estep2_variants_W4,
+                                 g_estep2_variants_W8, g_estep2_variants_W16};
+  const int ns[] = {g_estep2_variants_W1_n, g_estep2_variants_W2_n, g_estep2_variants_W4_n,
+                    g_estep2_variants_W8_n, g_estep2_variants_W16_n};
+  const char *force = getenv("MRLDA_ESTEP2_VARIANT");  // "NW,CPW[,RREG]" — profiling aid
+  int fw = 0, fc = 0, fr = 0;
+  if (force && sscanf(force, "%d,%d,%d", &fw, &fc, &fr) < 2) fw = fc = fr = 0;
+  const char *ew = getenv("MRLDA_ESTEP2_WPS");  // warps per SM class: 8 or 16
+  const int wps = ew ? atoi(ew) : MRLDA_DEFAULT_WPS;
+  const int max_cpw = wps == 16 ? 16 : 26;
+  // fewest warps per CTA whose column slice stays <= max_cpw doubles, then the narrowest slice
+  const Estep2Variant *best = nullptr;
+  for (int t = 0; t < 5; t++) {
+    for (int i = 0; i < ns[t]; i++) {
+      const Estep2Variant *v = &tabs[t][i];
+      if (v->NW * v->CPW < K) continue;
+      if (fw) {
+        if (v->NW == fw && v->CPW == fc && (fr ? v->RREG == fr : v->RREG == estep2_rreg(v->CPW, v->WPS)) &&
+            (!ew || v->WPS == wps))
+          return v;
+        continue;
+      }
+      if (v->WPS != wps || v->RREG != estep2_rreg(v->CPW, v->WPS)) continue;
+      if (!best || v->CPW < best->CPW) best = v;
+    }
+    if (best) {
+      if (best->CPW <= max_cpw) return best;
+      if (t < 4) best = nullptr;  // slice too wide at this warp count: try more warps
+    }
+  }
+  return best;
+}
+
 extern "C" {
 
 const char *mrlda_version(void) { return "mrlda_b200 0.1 (sm_100a, fp64)"; }
@@ -502,7 +544,7 @@ void mrlda_destroy(mrlda_ctx *ctx) {
                   ctx->d_gamma,   ctx->d_alpha,  ctx->d_lik_alpha, ctx->d_logbeta, ctx->d_E,
                   ctx->d_rowmax,  ctx->d_dl,     ctx->d_stats,    ctx->d_nrm,    ctx->d_present,
                   ctx->d_alpha_ss, ctx->d_counters, ctx->d_work,  ctx->d_partial, ctx->d_colsum,
-                  ctx->d_alpha_work};
+                  ctx->d_alpha_work, ctx->d_phase};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &e : ctx->ev)
@@ -550,6 +592,9 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
     return MRLDA_EUNSUPPORTED;
   }
   ctx->KS = ctx->variant->L * ctx->variant->KPL;
+  ctx->variant2 = select_variant2(ctx->K);
+  ctx->ES = ctx->KS;
+  if (ctx->variant2) ctx->ES = std::max(ctx->ES, ctx->variant2->NW * ctx->variant2->CPW);
   auto fail = [&](int code) {
     g_global_error = ctx->err;
     mrlda_destroy(ctx);
@@ -575,7 +620,7 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   for (auto &ev : ctx->ev) CKC(cudaEventCreate(&ev));
-  const size_t K = ctx->K, V = ctx->V, KS = ctx->KS;
+  const size_t K = ctx->K, V = ctx->V, KS = ctx->ES;
   CKC(cudaMalloc(&ctx->d_alpha, K * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_lik_alpha, sizeof(double)));
   CKC(cudaMalloc(&ctx->d_logbeta, V * K * sizeof(double)));
@@ -588,6 +633,8 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   CKC(cudaMalloc(&ctx->d_alpha_ss, K * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_counters, 4 * sizeof(long long)));
   CKC(cudaMalloc(&ctx->d_work, 4 * sizeof(int)));
+  CKC(cudaMalloc(&ctx->d_phase, 16 * sizeof(long long)));
+  CKC(cudaMemset(ctx->d_phase, 0, 16 * sizeof(long long)));
   ctx->slab = 256;
   ctx->nslabs = (int)((V + ctx->slab - 1) / ctx->slab);
   CKC(cudaMalloc(&ctx->d_partial, (size_t)ctx->nslabs * K * sizeof(double)));
@@ -609,7 +656,7 @@ static int refresh_rows(mrlda_ctx *ctx) {
   int64_t blocks = ((int64_t)ctx->V * 32 + threads - 1) / threads;
   expand_rows_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(ctx->d_logbeta, ctx->d_E,
                                                                      ctx->d_rowmax, ctx->V, ctx->K,
-                                                                     ctx->KS);
+                                                                     ctx->ES);
   ctx->launches++;
   CK(cudaGetLastError());
   return MRLDA_OK;
@@ -662,6 +709,8 @@ int mrlda_set_corpus_csr(mrlda_ctx *ctx, int64_t n_docs, const int64_t *row_ptr,
   std::stable_sort(order.begin(), order.end(),
                    [&](int32_t a, int32_t b) { return nnz[a] > nnz[b]; });
   ctx->max_rows = D ? nnz[order[0]] : 0;
+  ctx->h_nnz_sorted.resize((size_t)D);
+  for (int64_t i = 0; i < D; i++) ctx->h_nnz_sorted[i] = nnz[order[i]];
   ctx->p90_rows = D ? nnz[order[(size_t)(D / 10)]] : 0;
 
   CK(cudaSetDevice(ctx->cfg.device));
@@ -934,10 +983,6 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   CK(cudaMemcpyAsync(ctx->d_counters, hc, sizeof hc, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(int), st));
 
-  int c, t, cap;
-  size_t smem;
-  plan_estep(ctx, &c, &t, &cap, &smem);
-  CK(ctx->variant->prepare(smem));
   EstepArgs a;
   a.row_ptr = ctx->d_row_ptr;
   a.term_id = ctx->d_term;
@@ -946,6 +991,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.doc_tokens = ctx->d_tokens;
   a.n_docs = ctx->D;
   a.E = ctx->d_E;
+  a.e_stride = ctx->ES;
   a.rowmax = ctx->d_rowmax;
   a.logbeta = ctx->d_logbeta;
   a.alpha = ctx->d_alpha;
@@ -954,17 +1000,64 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.stats = ctx->cfg.learning ? ctx->d_stats : nullptr;
   a.alpha_ss = ctx->d_alpha_ss;
   a.ll_counter = reinterpret_cast<unsigned long long *>(ctx->d_counters);
-  a.work_counter = ctx->d_work;
   a.slow_rows = ctx->d_work + 1;
+  a.phase_cycles = ctx->d_phase;
+  {
+    const char *rs = getenv("MRLDA_ESTEP2_RS");  // profiling aid: 1 = shared-memory transpose
+    a.rs_smem = rs ? atoi(rs) : 0;
+  }
   a.K = K;
   a.sweeps = ctx->cfg.sweep_cap - 1;
   a.use_stored_gamma = (ctx->gamma_valid && !ctx->cfg.random_start) ? 1 : 0;
   a.learning = ctx->cfg.learning ? 1 : 0;
-  a.cap_rows = cap;
-  int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, std::max<int64_t>(ctx->D, 1));
+
+  // Documents are sorted by distinct-term count, longest first.  Those that fit one SM's registers +
+  // shared memory go to the register-stationary kernel; the longer head of the order goes to the
+  // general kernel, which streams the rows beyond its shared-memory tile from L2.
+  int n_long = (int)ctx->D;
+  int cap2 = 0, grid2 = 0;
+  const char *fk = getenv("MRLDA_ESTEP_KERNEL");  // "1": general kernel only (test / profiling aid)
+  const bool use2 = ctx->variant2 && !(fk && atoi(fk) == 1);
+  if (use2 && ctx->D > 0) {
+    const Estep2Variant *v2 = ctx->variant2;
+    const int c2 = v2->WPS / v2->NW;
+    const size_t per = std::min(((size_t)233472 - (size_t)c2 * 1024) / c2, ctx->smem_optin) & ~(size_t)15;
+    int rsm = 0;
+    while (v2->smem_bytes(rsm + 1, 32 * (v2->RREG + rsm + 1)) <= per) rsm++;
+    // one shared-memory slot doubles as the transpose scratch of the S reduction; documents that
+    // need it for rows fall back to the in-register reduce-scatter
+    const int need_slots = (ctx->max_rows + 31) / 32;
+    if (v2->RREG + rsm > need_slots + 1) rsm = std::max(1, need_slots + 1 - v2->RREG);
+    cap2 = 32 * (v2->RREG + rsm);
+    if (rsm >= 1 && v2->smem_bytes(rsm, cap2) <= per) {
+      n_long = (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), cap2,
+                                      [](int cap, int32_t nn) { return cap >= nn; }) -
+                     ctx->h_nnz_sorted.begin());
+      grid2 = (int)std::min<int64_t>((int64_t)c2 * ctx->num_sms, ctx->D - n_long);
+      if (grid2 > 0) CK(v2->prepare(v2->smem_bytes(rsm, cap2)));
+    }
+  }
+  int c = 1, t = 32, cap = 2;
+  size_t smem = 0;
+  if (n_long > 0) {
+    plan_estep(ctx, &c, &t, &cap, &smem);
+    CK(ctx->variant->prepare(smem));
+  }
   CK(cudaEventRecord(ctx->ev[1], st));
-  if (ctx->D > 0) {
+  if (n_long > 0) {
+    a.doc_begin = 0;
+    a.doc_end = n_long;
+    a.work_counter = ctx->d_work;
+    a.cap_rows = cap;
+    int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, n_long);
     CK(ctx->variant->launch(a, grid, t, cap, st));
+    ctx->launches++;
+  }
+  if (grid2 > 0) {
+    a.doc_begin = n_long;
+    a.doc_end = (int)ctx->D;
+    a.work_counter = ctx->d_work + 2;
+    CK(ctx->variant2->launch(a, grid2, cap2, st));
     ctx->launches++;
   }
   CK(cudaEventRecord(ctx->ev[2], st));
@@ -1019,7 +1112,7 @@ int mrlda_m_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
     int64_t blocks = ((int64_t)V * 32 + threads - 1) / threads;
     finalize_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(ctx->d_stats, ctx->d_present,
                                                                 ctx->d_nrm, ctx->cfg.eta, V, K,
-                                                                ctx->KS, ctx->d_dl, ctx->d_logbeta,
+                                                                ctx->ES, ctx->d_dl, ctx->d_logbeta,
                                                                 ctx->d_E, ctx->d_rowmax);
   }
   ctx->launches += 3;
@@ -1136,6 +1229,14 @@ int mrlda_measure_fp64_peak(mrlda_ctx *ctx, double *tflops) {
   }
   cudaFree(buf);
   *tflops = best;
+  return MRLDA_OK;
+}
+
+int mrlda_debug_phase_cycles(mrlda_ctx *ctx, int64_t out[16]) {
+  if (!ctx || !out) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpy(out, ctx->d_phase, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+  CK(cudaMemset(ctx->d_phase, 0, 16 * sizeof(long long)));
   return MRLDA_OK;
 }
 

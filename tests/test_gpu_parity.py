@@ -59,8 +59,19 @@ def _check(out, ref, c, learning=True):
         assert rel_err(out["alpha"], ref["alpha"]) < TOL
 
 
-@pytest.mark.parametrize("K", [3, 8, 20, 33, 50, 100, 130, 200])
-def test_one_iteration_matches_oracle(capi, oracle, K):
+@pytest.fixture(params=["auto", "general"])
+def kernel_mode(request, monkeypatch):
+    """auto: register-stationary kernel for documents that fit one SM, general kernel for the rest;
+    general: force the general (shared-memory tile + L2 streaming) kernel for every document."""
+    if request.param == "general":
+        monkeypatch.setenv("MRLDA_ESTEP_KERNEL", "1")
+    else:
+        monkeypatch.delenv("MRLDA_ESTEP_KERNEL", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("K", [3, 8, 20, 33, 50, 100, 130, 200, 256])
+def test_one_iteration_matches_oracle(capi, oracle, K, kernel_mode):
     from mrlda_b200 import corpus
     c = small_corpus(D=40, V=400, K=K, mean_len=50, seed=K)
     alpha = np.full(K, 1e-3)
@@ -100,7 +111,7 @@ def test_stats_are_phi_weighted_counts(capi, oracle):
     assert np.allclose(out["gamma"].sum(1), alpha.sum() + ntok, rtol=1e-12)
 
 
-def test_stored_gamma_and_random_start(capi, oracle):
+def test_stored_gamma_and_random_start(capi, oracle, kernel_mode):
     from mrlda_b200 import corpus
     K = 20
     c = small_corpus(D=30, V=300, K=K, seed=4)
@@ -137,7 +148,7 @@ def test_symmetric_alpha_iteration(capi, oracle):
     assert np.all(out["alpha"] == out["alpha"][0])
 
 
-def test_empty_and_single_token_documents(capi, oracle):
+def test_empty_and_single_token_documents(capi, oracle, kernel_mode):
     """null content is counted and skipped (DocumentMapper.java:178,197-201); 1-token documents."""
     from mrlda_b200 import corpus
     K, V = 8, 50
@@ -151,18 +162,25 @@ def test_empty_and_single_token_documents(capi, oracle):
 
 
 def test_long_documents_exceed_the_tile(capi, oracle):
-    """Documents with more distinct terms than the shared-memory tile holds stream rows from L2."""
+    """Documents with more distinct terms than one SM holds go to the general kernel and stream
+    rows from L2; shorter ones in the same corpus take the register-stationary kernel."""
     from mrlda_b200 import corpus
     K = 200
-    c = corpus.generate(6, 3000, K, 1500, seed=11)
-    assert np.diff(c.row_ptr).max() > 200
+    long_docs = corpus.generate(6, 3000, K, 1500, seed=11)
+    short_docs = corpus.generate(10, 3000, K, 150, seed=12)
+    n = np.concatenate([np.diff(long_docs.row_ptr), np.diff(short_docs.row_ptr)])
+    rp = np.zeros(len(n) + 1, dtype=np.int64)
+    rp[1:] = np.cumsum(n)
+    c = corpus.Corpus(rp, np.concatenate([long_docs.term_id, short_docs.term_id]),
+                      np.concatenate([long_docs.count, short_docs.count]), 3000, K)
+    assert np.diff(c.row_ptr).max() > 300 and np.diff(c.row_ptr).min() < 190
     alpha = np.full(K, 1e-3)
     lb = corpus.init_logbeta(c.n_terms, K, seed=7)
     out, ref = _run_pair(capi, oracle, c, alpha, lb, sweep_cap=8)
     _check(out, ref, c)
 
 
-def test_sparse_beta_takes_exact_slow_path(capi, oracle):
+def test_sparse_beta_takes_exact_slow_path(capi, oracle, kernel_mode):
     """A model where most (topic,term) cells are dead (lambda = eta => logbeta ~ -1e12) and the
     stored gamma points at the wrong topics: the linear-space norm underflows and the kernel must
     redo those rows in log space without NaNs."""
@@ -186,7 +204,7 @@ def test_sparse_beta_takes_exact_slow_path(capi, oracle):
     _check(out, ref, c)
 
 
-def test_three_em_iterations_track_oracle(capi, oracle):
+def test_three_em_iterations_track_oracle(capi, oracle, kernel_mode):
     """Per-iteration ELBO / logbeta / alpha parity over consecutive iterations (gamma carried)."""
     from mrlda_b200 import corpus
     K = 20
