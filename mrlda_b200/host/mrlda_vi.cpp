@@ -1,0 +1,332 @@
+// mrlda_vi.cpp — native stand-in for `hadoop jar Mr.LDA.jar cc.mrlda.VariationalInference ...`.
+//
+// Mirrors VariationalInference.run (VariationalInference.java:70-397) around the hot path: the same
+// options (VariationalInferenceOptions.java:55-273), the same model files (alpha-N, beta-N,
+// gamma-N/), the same gamma-directory rotation (:359-379), log lines (:257-275,381-384) and
+// convergence test (:383-386).  JobClient.runJob + the alpha update are one mrlda_iterate call.
+// Extensions (not in the reference): -device, -seed, -rank/-world/-ncclid for one process per GPU.
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/mrlda_b200.h"
+#include "model_io.hpp"
+
+using namespace mrlda_host;
+
+namespace {
+
+struct Options {
+  std::string input, output, model_path, informed_prior;
+  int topics = 0, terms = 0;
+  int iterations = 30;  // Settings.DEFAULT_GLOBAL_MAXIMUM_ITERATION
+  int mappers = 100, reducers = 50;
+  bool training = true, resume = false, random_start = false, symmetric = false, direct_emit = false;
+  int snapshot = 0;
+  int device = 0, rank = 0, world = 1;
+  unsigned long long seed = 0x4d724c4441ull;
+  std::string nccl_id_file;
+};
+
+void info(const std::string &s) { printf("INFO  VariationalInference: %s\n", s.c_str()); fflush(stdout); }
+
+[[noreturn]] void usage(const std::string &why) {
+  if (!why.empty()) fprintf(stderr, "ERROR %s\n", why.c_str());
+  fprintf(stderr,
+          "usage: cc.mrlda.VariationalInference\n"
+          " -directemit            disable in-mapper-combiner (accepted; statistics always sum over all documents)\n"
+          " -help                  print the help message\n"
+          " -input <path>          input file or directory\n"
+          " -iteration <int>       number of iterations (default - 30)\n"
+          " -mapper <int>          number of mappers (accepted, ignored)\n"
+          " -modelindex <int>      the iteration/index of current model parameters\n"
+          " -output <path>         output directory\n"
+          " -randomstart           start gamma from random point every iteration\n"
+          " -reducer <int>         number of reducers (accepted, ignored)\n"
+          " -symmetricalpha        symmetric topic Dirichlet prior\n"
+          " -term <int>            number of terms\n"
+          " -test <path>           run program in inference mode, i.e. test held-out likelihood\n"
+          " -topic <int>           number of topics\n"
+          " -device/-seed/-rank/-world/-ncclid  (extensions: GPU ordinal, beta seed, one process per GPU)\n");
+  exit(0);  // the reference prints the help and exits 0 on a parse error (VIO.java:251-266)
+}
+
+bool check(bool cond, const std::string &msg) {
+  if (!cond) usage(msg);
+  return cond;
+}
+
+Options parse(int argc, char **argv) {
+  Options o;
+  bool has_iter = false, has_test = false, has_index = false, has_sym = false;
+  std::string iter_arg;
+  auto need = [&](int &i) -> std::string {
+    if (i + 1 >= argc) usage(std::string("Missing argument for option: ") + argv[i]);
+    return argv[++i];
+  };
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    while (!a.empty() && a[0] == '-') a = a.substr(1);  // GnuParser accepts -opt and --opt
+    if (a == "help") usage("");
+    else if (a == "input") o.input = need(i);
+    else if (a == "output") o.output = need(i);
+    else if (a == "term") o.terms = atoi(need(i).c_str());
+    else if (a == "topic") o.topics = atoi(need(i).c_str());
+    else if (a == "iteration") { has_iter = true; iter_arg = need(i); }
+    else if (a == "mapper") o.mappers = atoi(need(i).c_str());
+    else if (a == "reducer") o.reducers = atoi(need(i).c_str());
+    else if (a == "test") { has_test = true; o.model_path = need(i); }
+    else if (a == "modelindex") { has_index = true; o.snapshot = atoi(need(i).c_str()); }
+    else if (a == "randomstart") o.random_start = true;
+    else if (a == "symmetricalpha") has_sym = true;
+    else if (a == "directemit") o.direct_emit = true;
+    else if (a == "truncatebeta") need(i);  // parsed, unused (VIO.java:116-120)
+    else if (a == "informedprior") o.informed_prior = need(i);
+    else if (a == "device") o.device = atoi(need(i).c_str());
+    else if (a == "seed") o.seed = strtoull(need(i).c_str(), nullptr, 10);
+    else if (a == "rank") o.rank = atoi(need(i).c_str());
+    else if (a == "world") o.world = atoi(need(i).c_str());
+    else if (a == "ncclid") o.nccl_id_file = need(i);
+    else usage("Unrecognized option: " + std::string(argv[i]));
+  }
+  check(!o.input.empty(), "Missing required option: input");
+  check(!o.output.empty(), "Missing required option: output");
+  if (o.output.back() != '/') o.output += '/';
+  // the reference evaluates -iteration while training is still true (VIO.java:141-150)
+  if (has_iter) {
+    o.iterations = atoi(iter_arg.c_str());
+    check(o.iterations > 0, "Illegal settings for iteration option: must be strictly positive...");
+  }
+  if (has_index && !has_test) {
+    o.resume = true;
+    check(o.snapshot < o.iterations,
+          "Option iteration and option modelindex do not agree with each other: option iteration "
+          "must be strictly larger than option modelindex...");
+  }
+  if (has_test) {
+    check(has_index, "Model index missing: modelindex was not initialized...");
+    if (o.model_path.back() != '/') o.model_path += '/';
+    o.training = false;
+    o.resume = false;
+  }
+  if (has_sym) {
+    check(o.training, "Option symmetricalpha ignored due to testing mode...");
+    check(!o.resume, "Option symmetricalpha ignored due to resume...");
+    o.symmetric = true;
+  }
+  check(o.topics > 0, "Illegal settings for topic option: must be strictly positive...");
+  check(o.terms > 0, "Illegal settings for term option: must be strictly positive...");
+  if (!o.training) o.random_start = false;  // "ignored in testing mode" (VIO.java:216-223)
+  check(o.mappers > 0, "Illegal settings for mapper option: must be strictly positive...");
+  check(o.informed_prior.empty(), "-informedprior is outside the scope of this build (SURVEY.md 8f-4)");
+  check(o.world >= 1 && o.rank >= 0 && o.rank < o.world, "bad -rank/-world");
+  return o;
+}
+
+void rm_rf(const std::string &p) {
+  if (!exists(p)) return;
+  if (is_dir(p)) {
+    DIR *d = opendir(p.c_str());
+    if (d) {
+      while (dirent *e = readdir(d)) {
+        std::string n = e->d_name;
+        if (n == "." || n == "..") continue;
+        rm_rf(p + (p.back() == '/' ? "" : "/") + n);
+      }
+      closedir(d);
+    }
+    rmdir(p.c_str());
+  } else {
+    unlink(p.c_str());
+  }
+}
+
+void mkdirs(const std::string &p) {
+  std::string cur;
+  for (size_t i = 0; i < p.size(); i++) {
+    cur.push_back(p[i]);
+    if (p[i] == '/' || i + 1 == p.size()) mkdir(cur.c_str(), 0777);
+  }
+}
+
+void die(mrlda_ctx *ctx, const char *what) {
+  fprintf(stderr, "ERROR %s: %s\n", what, mrlda_last_error(ctx));
+  exit(1);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+  Options o = parse(argc, argv);
+  const int K = o.topics, V = o.terms;
+  info("Tool: VariationalInference");
+  info(" - input path: " + o.input);
+  info(" - output path: " + o.output);
+  info(" - number of topics: " + std::to_string(K));
+  info(" - number of terms: " + std::to_string(V));
+  info(" - number of iterations: " + std::to_string(o.iterations));
+  info(" - number of mappers: " + std::to_string(o.mappers));
+  info(" - number of reducers: " + std::to_string(o.reducers));
+  info(std::string(" - training mode: ") + (o.training ? "true" : "false"));
+  info(std::string(" - random start gamma: ") + (o.random_start ? "true" : "false"));
+  info(std::string(" - resume training: ") + (o.resume ? "true" : "false"));
+  info(std::string(" - direct emit from mapper: ") + (o.direct_emit ? "true" : "false"));
+  info(std::string(" - symmetric alpha: ") + (o.symmetric ? "true" : "false"));
+
+  try {
+    // VariationalInference.java:111-116
+    if (o.rank == 0) {
+      if (!o.resume && exists(o.output)) rm_rf(o.output);
+      mkdirs(o.output);
+    }
+    std::string input_dir = o.input;
+    std::string alpha_dir, beta_dir;
+    const std::string alpha_path = o.output + "alpha-", beta_path = o.output + "beta-";
+    if (!o.training) {
+      alpha_dir = o.model_path + "alpha-" + std::to_string(o.snapshot);
+      beta_dir = o.model_path + "beta-" + std::to_string(o.snapshot);
+    } else if (!o.resume) {
+      alpha_dir = alpha_path + "0";
+      if (o.rank == 0) write_alpha(alpha_dir, std::vector<double>((size_t)K, 1e-3));  // :155-168
+    } else {
+      alpha_dir = alpha_path + std::to_string(o.snapshot);
+      beta_dir = beta_path + std::to_string(o.snapshot);
+      input_dir = o.output + "gamma-" + std::to_string(o.snapshot);
+    }
+
+    mrlda_config cfg;
+    mrlda_default_config(&cfg);
+    cfg.n_topics = K;
+    cfg.n_terms = V;
+    cfg.learning = o.training;
+    cfg.random_start = o.random_start;
+    cfg.symmetric_alpha = o.symmetric;
+    cfg.device = o.device;
+    cfg.rank = o.rank;
+    cfg.world_size = o.world;
+    cfg.seed = o.seed;
+    mrlda_ctx *ctx = nullptr;
+    if (mrlda_create(&cfg, &ctx) != MRLDA_OK) die(nullptr, "mrlda_create");
+
+    if (o.world > 1) {  // one process per GPU: rank 0 publishes the NCCL id through a file
+      check(!o.nccl_id_file.empty(), "-ncclid <file> is required with -world > 1");
+      uint8_t id[MRLDA_NCCL_ID_BYTES];
+      if (o.rank == 0) {
+        if (mrlda_nccl_unique_id(id) != MRLDA_OK) die(nullptr, "mrlda_nccl_unique_id");
+        FILE *f = fopen((o.nccl_id_file + ".tmp").c_str(), "wb");
+        fwrite(id, 1, sizeof id, f);
+        fclose(f);
+        rename((o.nccl_id_file + ".tmp").c_str(), o.nccl_id_file.c_str());
+      } else {
+        while (!exists(o.nccl_id_file)) std::this_thread::sleep_for(std::chrono::milliseconds(50));
+        FILE *f = fopen(o.nccl_id_file.c_str(), "rb");
+        if (!f || fread(id, 1, sizeof id, f) != sizeof id) usage("cannot read " + o.nccl_id_file);
+        fclose(f);
+      }
+      if (mrlda_comm_init(ctx, id) != MRLDA_OK) die(ctx, "mrlda_comm_init");
+    }
+
+    // the input split of this rank: contiguous documents balanced by nnz
+    Corpus all = read_corpus(input_dir, K, V);
+    int64_t lo = 0, hi = all.n_docs();
+    if (o.world > 1) {
+      const int64_t Z = all.row_ptr.back();
+      auto bound = [&](int r) -> int64_t {
+        if (r <= 0) return 0;
+        if (r >= o.world) return all.n_docs();
+        return std::lower_bound(all.row_ptr.begin(), all.row_ptr.end(), Z * r / o.world) -
+               all.row_ptr.begin();
+      };
+      lo = std::min(bound(o.rank), all.n_docs());
+      hi = std::min(std::max(bound(o.rank + 1), lo), all.n_docs());
+    }
+    std::vector<int64_t> rp((size_t)(hi - lo + 1));
+    for (int64_t d = lo; d <= hi; d++) rp[(size_t)(d - lo)] = all.row_ptr[d] - all.row_ptr[lo];
+    const int64_t z0 = all.row_ptr[lo];
+    const bool stored_gamma = !all.gamma.empty();
+    if (mrlda_set_corpus_csr(ctx, hi - lo, rp.data(), all.term_id.data() + z0, all.count.data() + z0,
+                             all.doc_id.data() + lo,
+                             stored_gamma ? all.gamma.data() + (size_t)lo * K : nullptr) != MRLDA_OK)
+      die(ctx, "mrlda_set_corpus_csr");
+
+    double last_ll = 0;
+    int iteration = o.snapshot;
+    bool model_loaded = false;
+    std::vector<double> gamma((size_t)(hi - lo) * K), dl((size_t)V * K), alpha((size_t)K);
+    std::vector<float> nrm((size_t)K);
+    std::vector<uint8_t> present((size_t)V);
+
+    do {
+      if (!model_loaded) {
+        if (iteration != 0) {  // VariationalInference.java:191-194
+          check(exists(beta_dir), "Missing model parameter beta...");
+          std::vector<double> bdl;
+          std::vector<float> bn;
+          std::vector<uint8_t> bp;
+          read_beta(beta_dir, K, V, bdl, bn, bp);
+          if (mrlda_set_beta(ctx, bdl.data(), bn.data(), bp.data()) != MRLDA_OK) die(ctx, "mrlda_set_beta");
+        } else {
+          // no beta file at iteration 0: every row is initialised lazily by retrieveBeta
+          if (mrlda_init_beta_random(ctx) != MRLDA_OK) die(ctx, "mrlda_init_beta_random");
+        }
+        check(exists(alpha_dir), "Missing model parameter alpha...");  // :195
+        std::vector<double> a0 = read_alpha(alpha_dir, K);
+        if (mrlda_set_alpha(ctx, a0.data()) != MRLDA_OK) die(ctx, "mrlda_set_alpha");
+        model_loaded = true;
+      }
+      auto t0 = std::chrono::steady_clock::now();
+      mrlda_iter_result res;
+      if (mrlda_iterate(ctx, &res) != MRLDA_OK) die(ctx, "mrlda_iterate");
+      double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      info("Iteration " + std::to_string(iteration + 1) + " finished in " + java_double(secs) + " seconds");
+      const double ll = res.log_likelihood;  // -counter / 1e6 (VariationalInference.java:261-262)
+      info("Log likelihood of the model is: " + java_double(ll));
+      info("Total number of documents is: " + std::to_string((int)res.n_docs));
+      info("Total number of terms is: " + std::to_string((int)res.n_terms_seen));
+      info("E-step " + java_double(res.e_step_ms) + " ms, all-reduce " + java_double(res.allreduce_ms) +
+           " ms, M-step " + java_double(res.m_step_ms) + " ms, alpha " + java_double(res.alpha_ms) +
+           " ms on the device");
+
+      if (o.training) {
+        if (mrlda_get_alpha(ctx, alpha.data()) != MRLDA_OK) die(ctx, "mrlda_get_alpha");
+        alpha_dir = alpha_path + std::to_string(iteration + 1);
+        if (mrlda_get_beta(ctx, dl.data(), nrm.data(), present.data()) != MRLDA_OK) die(ctx, "mrlda_get_beta");
+        beta_dir = beta_path + std::to_string(iteration + 1);
+        if (o.rank == 0) {
+          write_alpha(alpha_dir, alpha);  // :315-318
+          info("Successfully export new alpha vector to file " + alpha_dir);
+          write_beta(beta_dir, K, V, dl.data(), nrm.data(), present.data());  // :346-348
+        }
+      }
+      if (!o.random_start || !o.training) {  // :359-379
+        std::string gamma_dir = input_dir;
+        input_dir = o.output + "gamma-" + std::to_string(iteration + 1);
+        mkdirs(input_dir);
+        if (mrlda_get_gamma(ctx, gamma.data()) != MRLDA_OK) die(ctx, "mrlda_get_gamma");
+        char name[64];
+        snprintf(name, sizeof name, "/gamma_gamma-m-%05d", o.rank);
+        write_gamma(input_dir + name, all, lo, hi, gamma.data(), K);
+        if (iteration != 0 && o.rank == 0) rm_rf(gamma_dir);
+      }
+      info("Log likelihood after iteration " + std::to_string(iteration + 1) + " is " + java_double(ll));
+      if (std::fabs((last_ll - ll) / last_ll) <= 0.000001) {  // Settings.java:56
+        info("Model converged after " + std::to_string(iteration + 1) + " iterations...");
+        break;
+      }
+      last_ll = ll;
+      iteration++;
+    } while (iteration < o.iterations);
+    mrlda_destroy(ctx);
+  } catch (const std::exception &e) {
+    fprintf(stderr, "ERROR %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
