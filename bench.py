@@ -306,7 +306,8 @@ def main():
             "k1_ms": k1_ms_max, "allreduce_ms": ar_ms_max,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
                          "frac": ach / hbm, "traffic": None, "peak_source": how,
-                         "kernel": "estep_kernel<8,26>" if K == 200 else "estep_kernel",
+                         "kernel": "estep2_kernel<8,26,2,8> (+ estep_kernel<8,26> for documents above 192 rows)"
+                         if K == 200 else "estep2_kernel / estep_kernel",
                          "algorithmic_bytes_per_launch": B,
                          "note": "binding resource is the FP64 pipe, see fp64"},
             "fp64": {"achieved_tflops": F / (k1_ms_max * 1e-3) / 1e12, "peak_tflops": fp64_peak,
