@@ -26,6 +26,7 @@
 //     those of the last, partially filled slot.
 #pragma once
 #include "estep_kernel.cuh"
+#include "tmem_ops.cuh"
 
 #ifdef MRLDA_PHASE_TIMING
 #define MRLDA_TICK(i) tm[i] = clock64()
@@ -45,6 +46,17 @@ struct Estep2Shape {
   static_assert(NW == 1 || NW == 2 || NW == 4 || NW == 8 || NW == 16, "NW in {1,2,4,8,16}");
   static_assert((WPS == 8 || WPS == 16) && NW <= WPS, "WPS in {8,16}");
 };
+
+// TMEM slot stride in 32-bit columns: one tcgen05.ld.32x32b.xS fetches a slot (2*CPW words used)
+__host__ __device__ constexpr int estep2_tmem_stride(int cpw) {
+  return 2 * cpw > 32 ? 64 : (2 * cpw > 16 ? 32 : (2 * cpw > 8 ? 16 : 8));
+}
+// TMEM columns a CTA allocates (all co-resident CTAs together own the 512 columns of the SM) and
+// the slots each thread gets out of them (warps w and w+4 share a lane quarter and split columns)
+__host__ __device__ constexpr int estep2_tmem_cols(int nw, int wps) { return 512 / (wps / nw); }
+__host__ __device__ constexpr int estep2_tmem_slots(int nw, int cpw, int wps) {
+  return estep2_tmem_cols(nw, wps) / (nw > 4 ? nw / 4 : 1) / estep2_tmem_stride(cpw);
+}
 
 // register-resident slots: what fits in 255 registers next to the working set (theta or S: 2*CPW
 // registers, partial sums, addresses) without spilling E into local memory (-Xptxas -v)
@@ -68,9 +80,11 @@ __device__ __forceinline__ void estep2_sweep(
     const EstepArgs &a, double (&e)[RREG][CPW], const double *es, double *part, const double *cnt_s,
     double *r_s, int *flag_s, const double *theta_w, double (&s)[CPW], double &lik,
     unsigned &badbits, const int64_t b, const int n, const int nslots, const int cap_rows,
-    const int warp, const int lane, long long *tm) {
+    const int warp, const int lane, long long *tm, const uint32_t tbase, const int rt) {
   (void)tm;
-  constexpr int HALF = CPW / 2;
+  constexpr int HALF = CPW / 2, TS = estep2_tmem_stride(CPW);
+  // slot q lives in registers (q < RREG), in TMEM (q < RREG + rt) or in shared memory
+  const int nt_end = nslots < RREG + rt ? nslots : RREG + rt;
   const int K = a.K;
   // (2) partial dot products of my rows over my warp's columns.  Register slots are processed
   // unconditionally (an unused slot holds zeros) so that the chains of different slots interleave;
@@ -92,7 +106,7 @@ __device__ __forceinline__ void estep2_sweep(
 #pragma unroll
     for (int q = 0; q < RREG; q++) pw[32 * q] = acc[q][0] + acc[q][1];
   }
-  if (nslots > RREG) {  // slots that live in shared memory: theta held in registers for all of them
+  if (nslots > RREG) {  // slots outside the register file: theta held in registers for all of them
     double th[CPW];
 #pragma unroll
     for (int i = 0; i < HALF; i++) {
@@ -100,9 +114,29 @@ __device__ __forceinline__ void estep2_sweep(
       th[2 * i] = tv.x;
       th[2 * i + 1] = tv.y;
     }
-    for (int q = RREG; q < nslots; q++) {
+    // TMEM slots (a second load buffer for software pipelining does not fit the register file)
+    auto dot_words = [&](const uint32_t (&w32)[TS]) -> double {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < HALF; i += 2) {
+        a0 = fma(th[2 * i], __hiloint2double((int)w32[4 * i + 1], (int)w32[4 * i]), a0);
+        a1 = fma(th[2 * i + 1], __hiloint2double((int)w32[4 * i + 3], (int)w32[4 * i + 2]), a1);
+        if (i + 1 < HALF) {
+          a2 = fma(th[2 * i + 2], __hiloint2double((int)w32[4 * i + 5], (int)w32[4 * i + 4]), a2);
+          a3 = fma(th[2 * i + 3], __hiloint2double((int)w32[4 * i + 7], (int)w32[4 * i + 6]), a3);
+        }
+      }
+      return (a0 + a1) + (a2 + a3);
+    };
+    for (int q = RREG; q < nt_end; q++) {
+      uint32_t w32[TS];
+      TmemVec<TS>::ld(tbase + (uint32_t)(q - RREG) * TS, w32);
+      tmem_wait_ld();
+      pw[32 * q] = dot_words(w32);
+    }
+    for (int q = RREG + rt; q < nslots; q++) {  // shared-memory slots
       const double2 *src = reinterpret_cast<const double2 *>(es) +
-                           ((size_t)((q - RREG) * NW + warp) * HALF) * 32 + lane;
+                           ((size_t)((q - RREG - rt) * NW + warp) * HALF) * 32 + lane;
       double a0 = 0.0, a1 = 0.0;
 #pragma unroll
       for (int i = 0; i < HALF; i++) {
@@ -180,14 +214,41 @@ __device__ __forceinline__ void estep2_sweep(
       for (int q = 0; q < RREG; q++) scatter(q, r[q], e[q]);
     }
   }
-  for (int q = RREG; q < nslots; q++) {
+  // TMEM slots
+  auto s_words = [&](int q, const uint32_t (&w32)[TS]) {
+    double r = r_s[32 * q + lane];
+    if (r < 0.0) {
+      badbits |= 1u << q;
+      r = 0.0;
+    }
+    if (LAST) {
+      double tmp[CPW];
+#pragma unroll
+      for (int c = 0; c < CPW; c++) {
+        tmp[c] = __hiloint2double((int)w32[2 * c + 1], (int)w32[2 * c]);
+        s[c] = fma(r, tmp[c], s[c]);
+      }
+      scatter(q, r, tmp);
+    } else {
+#pragma unroll
+      for (int c = 0; c < CPW; c++)
+        s[c] = fma(r, __hiloint2double((int)w32[2 * c + 1], (int)w32[2 * c]), s[c]);
+    }
+  };
+  for (int q = RREG; q < nt_end; q++) {
+    uint32_t w32[TS];
+    TmemVec<TS>::ld(tbase + (uint32_t)(q - RREG) * TS, w32);
+    tmem_wait_ld();
+    s_words(q, w32);
+  }
+  for (int q = RREG + rt; q < nslots; q++) {  // shared-memory slots
     double r = r_s[32 * q + lane];
     if (r < 0.0) {
       badbits |= 1u << q;
       r = 0.0;
     }
     const double2 *src = reinterpret_cast<const double2 *>(es) +
-                         ((size_t)((q - RREG) * NW + warp) * HALF) * 32 + lane;
+                         ((size_t)((q - RREG - rt) * NW + warp) * HALF) * 32 + lane;
     double tmp[CPW];
 #pragma unroll
     for (int i = 0; i < HALF; i++) {
@@ -208,8 +269,10 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int K = a.K;
-  const int cap_rows = a.cap_rows;          // 32 * (RREG + rsm)
-  const int rsm = cap_rows / 32 - RREG;
+  constexpr int TS = estep2_tmem_stride(CPW);
+  const int rt = a.tmem_slots;              // slots per thread in TMEM (0: TMEM not used)
+  const int cap_rows = a.cap_rows;          // 32 * (RREG + rt + rsm)
+  const int rsm = cap_rows / 32 - RREG - rt;
 
   double *es = smem;                                        // rsm x NW x HALF x 32 double2
   double *part_s = es + (size_t)rsm * NW * 32 * CPW;        // 2 x NW x cap_rows
@@ -219,7 +282,19 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
   double *gam_s = theta_s + KS;                             // KS
   double *gextra_s = gam_s + KS;                            // KS
   double *red_s = gextra_s + KS;                            // 96: 3 x 16 sums, then doc meta
-  int *meta_s = reinterpret_cast<int *>(red_s + 64);        // [0] document, [1] slow-path flag
+  int *meta_s = reinterpret_cast<int *>(red_s + 64);        // [0] document, [1] slow-path flag, [2] TMEM base
+
+  // TMEM: this CTA's share of the SM's 512 columns, thread-private slots (tmem_ops.cuh)
+  uint32_t tbase = 0;
+  if (rt > 0) {
+    if (warp == 0) tmem_alloc(reinterpret_cast<uint32_t *>(meta_s + 2), estep2_tmem_cols(NW, WPS));
+    tmem_fence_before_sync();
+    __syncthreads();
+    tmem_fence_after_sync();
+    const uint32_t cols_per_thread = estep2_tmem_cols(NW, WPS) / (NW > 4 ? NW / 4 : 1);
+    tbase = (uint32_t)meta_s[2] + (((uint32_t)(warp & 3) * 32u) << 16) +
+            (uint32_t)(warp >> 2) * cols_per_thread;
+  }
 
   // Lane c owns column c of its warp (gamma_c, alpha_c, theta_c live in its registers).  The
   // register reduce-scatter leaves column rs_col in this lane; rs_src is the lane that ends up
@@ -282,9 +357,31 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         for (int c = 0; c < CPW; c++) e[q][c] = 0.0;
       }
     }
-    for (int q = RREG; q < nslots; q++) {
+    const int nt_end = nslots < RREG + rt ? nslots : RREG + rt;
+    for (int q = RREG; q < nt_end; q++) {  // TMEM slots
       const int row = 32 * q + lane;
-      double2 *dst = reinterpret_cast<double2 *>(es) + ((size_t)((q - RREG) * NW + warp) * HALF) * 32 + lane;
+      uint32_t w32[TS];
+#pragma unroll
+      for (int i = 0; i < TS; i++) w32[i] = 0u;
+      if (row < n) {
+        const double2 *src = reinterpret_cast<const double2 *>(
+            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+#pragma unroll
+        for (int i = 0; i < HALF; i++) {
+          const double2 v = __ldg(src + i);
+          w32[4 * i] = (uint32_t)__double2loint(v.x);
+          w32[4 * i + 1] = (uint32_t)__double2hiint(v.x);
+          w32[4 * i + 2] = (uint32_t)__double2loint(v.y);
+          w32[4 * i + 3] = (uint32_t)__double2hiint(v.y);
+        }
+      }
+      TmemVec<TS>::st(tbase + (uint32_t)(q - RREG) * TS, w32);
+    }
+    if (nt_end > RREG) tmem_wait_st();
+    for (int q = RREG + rt; q < nslots; q++) {  // shared-memory slots
+      const int row = 32 * q + lane;
+      double2 *dst = reinterpret_cast<double2 *>(es) +
+                     ((size_t)((q - RREG - rt) * NW + warp) * HALF) * 32 + lane;
       if (row < n) {
         const double2 *src = reinterpret_cast<const double2 *>(
             a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
@@ -325,15 +422,15 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       double *part = part_s + (size_t)(sweep & 1) * NW * cap_rows;
       if (!last)
         estep2_sweep<NW, CPW, RREG, false>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
-                                           badbits, b, n, nslots, cap_rows, warp, lane, tm);
+                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt);
       else
         estep2_sweep<NW, CPW, RREG, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
-                                          badbits, b, n, nslots, cap_rows, warp, lane, tm);
+                                          badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt);
       MRLDA_TICK(6);
       // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
       // document leaves it free, else reduce-scatter in registers
       double S_c;
-      if (a.rs_smem && nslots < RREG + rsm) {
+      if (a.rs_smem && rsm > 0 && nslots < RREG + rt + rsm) {
         double *scr = es + ((size_t)(rsm - 1) * NW + warp) * 32 * CPW;
 #pragma unroll
         for (int c = 0; c < CPW; c++) scr[c * 32 + lane] = s[c];
@@ -457,11 +554,16 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
   }
   // DocumentMapper.close (DocumentMapper.java:354-361)
   if (owner && ss_acc != 0.0) atomicAdd(a.alpha_ss + col, ss_acc);
+  if (rt > 0) {
+    tmem_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc((uint32_t)meta_s[2], estep2_tmem_cols(NW, WPS));
+  }
 }
 
 struct Estep2Variant {
   int NW, CPW, RREG, WPS;
-  cudaError_t (*launch)(const EstepArgs &, int grid, int cap_rows, cudaStream_t);
+  cudaError_t (*launch)(const EstepArgs &, int grid, int cap_rows, size_t smem, cudaStream_t);
   size_t (*smem_bytes)(int rsm, int cap_rows);
   cudaError_t (*prepare)(size_t smem);
 };
@@ -476,10 +578,10 @@ static cudaError_t variant2_prepare(size_t smem) {
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 template <int NW, int CPW, int RREG, int WPS>
-static cudaError_t variant2_launch(const EstepArgs &args, int grid, int cap_rows, cudaStream_t st) {
+static cudaError_t variant2_launch(const EstepArgs &args, int grid, int cap_rows, size_t smem,
+                                   cudaStream_t st) {
   EstepArgs a = args;
   a.cap_rows = cap_rows;
-  size_t smem = estep2_smem_bytes<NW, CPW>(cap_rows / 32 - RREG, cap_rows);
   estep2_kernel<NW, CPW, RREG, WPS><<<grid, NW * 32, smem, st>>>(a);
   return cudaGetLastError();
 }

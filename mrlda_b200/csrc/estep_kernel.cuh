@@ -62,6 +62,7 @@ struct EstepArgs {
   int use_stored_gamma;
   int learning;
   int cap_rows;  // tile capacity in rows (multiple of RPB)
+  int tmem_slots;  // register-stationary kernel: slots per thread kept in Tensor Memory
   int rs_smem;   // register-stationary kernel: transpose S through shared memory (1) or shuffles (0)
 };
 

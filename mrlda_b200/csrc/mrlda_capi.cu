@@ -1002,6 +1002,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.ll_counter = reinterpret_cast<unsigned long long *>(ctx->d_counters);
   a.slow_rows = ctx->d_work + 1;
   a.phase_cycles = ctx->d_phase;
+  a.tmem_slots = 0;
   {
     const char *rs = getenv("MRLDA_ESTEP2_RS");  // profiling aid: 1 = shared-memory transpose
     a.rs_smem = rs ? atoi(rs) : 0;
@@ -1016,25 +1017,33 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   // general kernel, which streams the rows beyond its shared-memory tile from L2.
   int n_long = (int)ctx->D;
   int cap2 = 0, grid2 = 0;
+  size_t smem2 = 0;
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");  // "1": general kernel only (test / profiling aid)
   const bool use2 = ctx->variant2 && !(fk && atoi(fk) == 1);
   if (use2 && ctx->D > 0) {
     const Estep2Variant *v2 = ctx->variant2;
     const int c2 = v2->WPS / v2->NW;
     const size_t per = std::min(((size_t)233472 - (size_t)c2 * 1024) / c2, ctx->smem_optin) & ~(size_t)15;
-    int rsm = 0;
-    while (v2->smem_bytes(rsm + 1, 32 * (v2->RREG + rsm + 1)) <= per) rsm++;
-    // one shared-memory slot doubles as the transpose scratch of the S reduction; documents that
-    // need it for rows fall back to the in-register reduce-scatter
+    // slot hierarchy per thread: RREG in registers, then Tensor Memory, then shared memory
+    const char *et = getenv("MRLDA_ESTEP2_TMEM");  // "0" disables TMEM slots (profiling aid)
     const int need_slots = (ctx->max_rows + 31) / 32;
-    if (v2->RREG + rsm > need_slots + 1) rsm = std::max(1, need_slots + 1 - v2->RREG);
-    cap2 = 32 * (v2->RREG + rsm);
-    if (rsm >= 1 && v2->smem_bytes(rsm, cap2) <= per) {
+    int rt = (et && atoi(et) == 0) ? 0 : estep2_tmem_slots(v2->NW, v2->CPW, v2->WPS);
+    rt = std::max(0, std::min(rt, need_slots - v2->RREG));
+    int rsm = 0;
+    while (v2->smem_bytes(rsm + 1, 32 * (v2->RREG + rt + rsm + 1)) <= per) rsm++;
+    rsm = std::max(0, std::min(rsm, need_slots - v2->RREG - rt));
+    cap2 = 32 * (v2->RREG + rt + rsm);
+    a.tmem_slots = rt;
+    if (v2->smem_bytes(rsm, cap2) <= per) {
       n_long = (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), cap2,
                                       [](int cap, int32_t nn) { return cap >= nn; }) -
                      ctx->h_nnz_sorted.begin());
       grid2 = (int)std::min<int64_t>((int64_t)c2 * ctx->num_sms, ctx->D - n_long);
-      if (grid2 > 0) CK(v2->prepare(v2->smem_bytes(rsm, cap2)));
+      // never let more than c2 CTAs share an SM: they would over-subscribe its 512 TMEM columns
+      // and the extra CTA's tcgen05.alloc would wait forever
+      const size_t min_dyn = (size_t)233472 / (c2 + 1) - 1024 + 16;
+      smem2 = std::max(v2->smem_bytes(rsm, cap2), std::min(min_dyn, per));
+      if (grid2 > 0) CK(v2->prepare(smem2));
     }
   }
   int c = 1, t = 32, cap = 2;
@@ -1057,7 +1066,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
     a.doc_begin = n_long;
     a.doc_end = (int)ctx->D;
     a.work_counter = ctx->d_work + 2;
-    CK(ctx->variant2->launch(a, grid2, cap2, st));
+    CK(ctx->variant2->launch(a, grid2, cap2, smem2, st));
     ctx->launches++;
   }
   CK(cudaEventRecord(ctx->ev[2], st));
