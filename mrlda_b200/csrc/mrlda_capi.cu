@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/mrlda_b200.h"
@@ -415,6 +416,7 @@ struct mrlda_ctx {
 
   // corpus
   int64_t D = 0, Z = 0, n_tokens = 0;
+  size_t cap_D = 0, cap_Z = 0;  // capacity of the corpus buffers
   int64_t *d_row_ptr = nullptr;
   int32_t *d_term = nullptr, *d_count = nullptr, *d_order = nullptr, *d_tokens = nullptr;
   double *d_gamma = nullptr;
@@ -676,57 +678,28 @@ int mrlda_set_corpus_csr(mrlda_ctx *ctx, int64_t n_docs, const int64_t *row_ptr,
     set_err(ctx, "mrlda_set_corpus_csr: null term_id/count");
     return MRLDA_EINVAL;
   }
-  std::vector<int32_t> tokens((size_t)D), order((size_t)D), nnz((size_t)D);
-  int64_t total_tokens = 0;
-  for (int64_t d = 0; d < D; d++) {
-    int64_t b = row_ptr[d], e = row_ptr[d + 1];
-    if (e < b || e > Z) {
-      set_err(ctx, "mrlda_set_corpus_csr: row_ptr not monotone at document %lld", (long long)d);
-      return MRLDA_EINVAL;
-    }
-    int64_t t = 0;
-    for (int64_t z = b; z < e; z++) {
-      if (term_id[z] < 1 || term_id[z] > ctx->V) {
-        set_err(ctx, "mrlda_set_corpus_csr: term id %d outside [1,%d] (document %lld)", term_id[z],
-                ctx->V, (long long)d);
-        return MRLDA_EINVAL;
-      }
-      if (count[z] <= 0) {
-        set_err(ctx, "mrlda_set_corpus_csr: non-positive count (document %lld)", (long long)d);
-        return MRLDA_EINVAL;
-      }
-      t += count[z];
-    }
-    if (t > 0x7fffffff) {
-      set_err(ctx, "mrlda_set_corpus_csr: document %lld has more than 2^31 tokens", (long long)d);
-      return MRLDA_EINVAL;
-    }
-    tokens[d] = (int32_t)t;
-    nnz[d] = (int32_t)(e - b);
-    total_tokens += t;
-  }
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(),
-                   [&](int32_t a, int32_t b) { return nnz[a] > nnz[b]; });
-  ctx->max_rows = D ? nnz[order[0]] : 0;
-  ctx->h_nnz_sorted.resize((size_t)D);
-  for (int64_t i = 0; i < D; i++) ctx->h_nnz_sorted[i] = nnz[order[i]];
-  ctx->p90_rows = D ? nnz[order[(size_t)(D / 10)]] : 0;
-
   CK(cudaSetDevice(ctx->cfg.device));
-  void *olds[] = {ctx->d_row_ptr, ctx->d_term, ctx->d_count, ctx->d_order, ctx->d_tokens, ctx->d_gamma};
-  for (void *p : olds)
-    if (p) cudaFree(p);
-  ctx->d_row_ptr = nullptr;
-  ctx->d_term = ctx->d_count = ctx->d_order = ctx->d_tokens = nullptr;
-  ctx->d_gamma = nullptr;
+  // device buffers: reuse when the new corpus fits (the end-to-end path sets the corpus every call)
   const size_t K = ctx->K;
-  CK(cudaMalloc(&ctx->d_row_ptr, (size_t)(D + 1) * sizeof(int64_t)));
-  CK(cudaMalloc(&ctx->d_term, std::max<size_t>(1, (size_t)Z) * sizeof(int32_t)));
-  CK(cudaMalloc(&ctx->d_count, std::max<size_t>(1, (size_t)Z) * sizeof(int32_t)));
-  CK(cudaMalloc(&ctx->d_order, std::max<size_t>(1, (size_t)D) * sizeof(int32_t)));
-  CK(cudaMalloc(&ctx->d_tokens, std::max<size_t>(1, (size_t)D) * sizeof(int32_t)));
-  CK(cudaMalloc(&ctx->d_gamma, std::max<size_t>(1, (size_t)D * K) * sizeof(double)));
+  if ((size_t)D > ctx->cap_D || (size_t)Z > ctx->cap_Z) {
+    void *olds[] = {ctx->d_row_ptr, ctx->d_term, ctx->d_count, ctx->d_order, ctx->d_tokens, ctx->d_gamma};
+    for (void *p : olds)
+      if (p) cudaFree(p);
+    ctx->d_row_ptr = nullptr;
+    ctx->d_term = ctx->d_count = ctx->d_order = ctx->d_tokens = nullptr;
+    ctx->d_gamma = nullptr;
+    ctx->cap_D = ctx->cap_Z = 0;
+    ctx->D = 0;
+    CK(cudaMalloc(&ctx->d_row_ptr, (size_t)(D + 1) * sizeof(int64_t)));
+    CK(cudaMalloc(&ctx->d_term, std::max<size_t>(1, (size_t)Z) * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_count, std::max<size_t>(1, (size_t)Z) * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_order, std::max<size_t>(1, (size_t)D) * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_tokens, std::max<size_t>(1, (size_t)D) * sizeof(int32_t)));
+    CK(cudaMalloc(&ctx->d_gamma, std::max<size_t>(1, (size_t)D * K) * sizeof(double)));
+    ctx->cap_D = (size_t)D;
+    ctx->cap_Z = (size_t)Z;
+  }
+  // start the bulk copies first; the host-side checks below overlap with them
   CK(cudaMemcpyAsync(ctx->d_row_ptr, row_ptr, (size_t)(D + 1) * sizeof(int64_t),
                      cudaMemcpyHostToDevice, ctx->stream));
   if (Z) {
@@ -735,21 +708,85 @@ int mrlda_set_corpus_csr(mrlda_ctx *ctx, int64_t n_docs, const int64_t *row_ptr,
     CK(cudaMemcpyAsync(ctx->d_count, count, (size_t)Z * sizeof(int32_t), cudaMemcpyHostToDevice,
                        ctx->stream));
   }
+  if (gamma0 && D)
+    CK(cudaMemcpyAsync(ctx->d_gamma, gamma0, (size_t)D * K * sizeof(double), cudaMemcpyHostToDevice,
+                       ctx->stream));
+  else  // documents without content never get a gamma (DocumentMapper.java:197-201): keep them 0
+    CK(cudaMemsetAsync(ctx->d_gamma, 0, std::max<size_t>(1, (size_t)D * K) * sizeof(double), ctx->stream));
+
+  // validation + per-document token counts, on all host cores
+  std::vector<int32_t> tokens((size_t)D), order((size_t)D), nnz((size_t)D);
+  const int nthr = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  std::vector<int64_t> part_tokens((size_t)nthr, 0), bad_doc((size_t)nthr, -1);
+  std::vector<int> bad_kind((size_t)nthr, 0);
+  const int V = ctx->V;
+  auto work = [&](int t) {
+    const int64_t d0 = D * t / nthr, d1 = D * (t + 1) / nthr;
+    int64_t tot = 0;
+    for (int64_t d = d0; d < d1; d++) {
+      const int64_t b = row_ptr[d], e = row_ptr[d + 1];
+      if (e < b || e > Z) {
+        bad_doc[t] = d;
+        bad_kind[t] = 1;
+        return;
+      }
+      int64_t tk = 0;
+      int flag = 0;
+      for (int64_t z = b; z < e; z++) {
+        flag |= (term_id[z] < 1) | (term_id[z] > V) | ((count[z] <= 0) << 1);
+        tk += count[z];
+      }
+      if (flag || tk > 0x7fffffff) {
+        bad_doc[t] = d;
+        bad_kind[t] = (flag & 1) ? 2 : ((flag & 2) ? 3 : 4);
+        return;
+      }
+      tokens[d] = (int32_t)tk;
+      nnz[d] = (int32_t)(e - b);
+      tot += tk;
+    }
+    part_tokens[t] = tot;
+  };
+  if (D * 4 + Z < (1 << 16) || nthr == 1) {
+    for (int t = 0; t < nthr; t++) work(t);
+  } else {
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthr; t++) pool.emplace_back(work, t);
+    for (auto &th : pool) th.join();
+  }
+  int64_t total_tokens = 0;
+  for (int t = 0; t < nthr; t++) {
+    if (bad_doc[t] >= 0) {
+      static const char *why[] = {"", "row_ptr not monotone", "term id outside [1, n_terms]",
+                                  "non-positive count", "more than 2^31 tokens"};
+      cudaStreamSynchronize(ctx->stream);
+      ctx->D = 0;
+      set_err(ctx, "mrlda_set_corpus_csr: %s in document %lld", why[bad_kind[t]], (long long)bad_doc[t]);
+      return MRLDA_EINVAL;
+    }
+    total_tokens += part_tokens[t];
+  }
+  // documents by distinct-term count, longest first (stable): counting sort
+  {
+    int32_t mx = 0;
+    for (int64_t d = 0; d < D; d++) mx = std::max(mx, nnz[d]);
+    std::vector<int64_t> start((size_t)mx + 2, 0);
+    for (int64_t d = 0; d < D; d++) start[(size_t)(mx - nnz[d]) + 1]++;
+    for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+    for (int64_t d = 0; d < D; d++) order[(size_t)start[(size_t)(mx - nnz[d])]++] = (int32_t)d;
+  }
+  ctx->max_rows = D ? nnz[order[0]] : 0;
+  ctx->p90_rows = D ? nnz[order[(size_t)(D / 10)]] : 0;
+  ctx->h_nnz_sorted.resize((size_t)D);
+  for (int64_t i = 0; i < D; i++) ctx->h_nnz_sorted[i] = nnz[order[i]];
+
   if (D) {
     CK(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)D * sizeof(int32_t),
                        cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_tokens, tokens.data(), (size_t)D * sizeof(int32_t),
                        cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (gamma0 && D) {
-    CK(cudaMemcpyAsync(ctx->d_gamma, gamma0, (size_t)D * K * sizeof(double), cudaMemcpyHostToDevice,
-                       ctx->stream));
-    ctx->gamma_valid = true;
-  } else {
-    CK(cudaMemsetAsync(ctx->d_gamma, 0, std::max<size_t>(1, (size_t)D * K) * sizeof(double),
-                       ctx->stream));
-    ctx->gamma_valid = false;
-  }
+  ctx->gamma_valid = gamma0 && D;
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->D = D;
   ctx->Z = Z;
