@@ -74,6 +74,19 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(self.samples)}
 
 
+def measured_traffic(workload, n_gpus):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/r1_traffic.json); None when no capture exists for this workload / GPU count."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    if t.get("workload") != workload or t.get("n_gpus") != n_gpus:
+        return None
+    return t["dram_bytes_read"] + t["dram_bytes_write"]
+
+
 def algorithmic_bytes(Z, D, K, s=8):
     """B_E = Z(8 + 2Ks) + 2DKs + 8(D+1)  (SURVEY.md section 8d)."""
     return Z * (8 + 2 * K * s) + 2 * D * K * s + 8 * (D + 1)
@@ -305,7 +318,9 @@ def main():
             "device_ms_per_step": dev_ms_max / args.steps,
             "k1_ms": k1_ms_max, "allreduce_ms": ar_ms_max,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                         "frac": ach / hbm, "traffic": None, "peak_source": how,
+                         "frac": ach / hbm,
+                         "traffic": measured_traffic(args.workload, world) if args.scale == 1.0 else None,
+                         "peak_source": how,
                          "kernel": "estep2_kernel<8,26,2,8> (+ estep_kernel<8,26> for documents above 192 rows)"
                          if K == 200 else "estep2_kernel / estep_kernel",
                          "algorithmic_bytes_per_launch": B,
