@@ -98,6 +98,14 @@ int mrlda_io_read_beta(const char *path, int32_t k, int32_t v, double *dl, float
         memcpy(dl, d.data(), d.size() * 8); memcpy(nrm, n.data(), n.size() * 4); memcpy(present, p.data(), p.size());
         return 0;)
 }
+// term index file of ParseCorpus: SequenceFile<IntWritable, Text> (ids 1..n, '\n'-separated terms)
+int mrlda_io_write_term_index(const char *path, int32_t n, const char *terms_nl) {
+  GUARD(SeqWriter w(path, kIntWritable, "org.apache.hadoop.io.Text"); const char *p = terms_nl;
+        for (int32_t i = 1; i <= n; i++) {
+          const char *e = strchr(p, '\n'); std::string t = e ? std::string(p, e) : std::string(p);
+          ByteWriter k, v; k.i32(i); v.text(t); w.append(k, v); p = e ? e + 1 : p + t.size();
+        } return 0;)
+}
 // java.lang.Double.toString, for the likelihood log lines
 int mrlda_io_java_double(double d, char *out, int32_t cap) {
   std::string s = java_double(d);

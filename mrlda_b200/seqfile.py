@@ -39,6 +39,7 @@ def load():
         L.mrlda_io_write_beta.argtypes = [C.c_char_p, C.c_int32, C.c_int32, _dp, _fp, _bp]
         L.mrlda_io_read_beta.argtypes = [C.c_char_p, C.c_int32, C.c_int32, _dp, _fp, _bp]
         L.mrlda_io_java_double.argtypes = [C.c_double, C.c_char_p, C.c_int32]
+        L.mrlda_io_write_term_index.argtypes = [C.c_char_p, C.c_int32, C.c_char_p]
         _lib = L
     return _lib
 
@@ -146,3 +147,8 @@ def java_double(x):
     buf = C.create_string_buffer(64)
     _ck(load().mrlda_io_java_double(float(x), buf, 64))
     return buf.value.decode()
+
+
+def write_term_index(path, terms):
+    """ParseCorpus's term index: SequenceFile<IntWritable, Text>, ids 1..len(terms)."""
+    _ck(load().mrlda_io_write_term_index(os.fsencode(path), len(terms), "\n".join(terms).encode()))

@@ -113,3 +113,26 @@ def test_java_double_to_string():
                     (0.001, "0.001"), (1e-4, "1.0E-4"), (1.0, "1.0"), (12345678.0, "1.2345678E7"),
                     (100.0, "100.0"), (0.5, "0.5"), (-0.0, "-0.0"), (2.5e-7, "2.5E-7")]:
         assert seqfile.java_double(x) == want
+
+
+def test_display_tools_read_model_files(tmp_path):
+    """DisplayTopic / DisplayDocument counterparts read what the codecs write
+    (DisplayTopic.java:97-142, DisplayDocument.java:87-100)."""
+    import subprocess
+    tool = os.path.join(os.path.dirname(os.path.dirname(__file__)), "mrlda_b200", "host", "mrlda-display")
+    K, V = 2, 5
+    dl = np.array([[-1.0, -9.0], [-2.0, -8.0], [-3.0, -7.5], [-4.0, -6.0], [-5.0, -5.5]])
+    beta, index = str(tmp_path / "beta-1"), str(tmp_path / "term")
+    seqfile.write_beta(beta, dl, np.zeros(K, dtype=np.float32), np.ones(V, dtype=np.uint8))
+    seqfile.write_term_index(index, ["alpha", "beta", "gamma", "delta", "eps"])
+    out = subprocess.run([tool, "topic", "-input", beta, "-index", index, "-topdisplay", "2"],
+                         capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[1] == "Top ranked 2 terms for Topic 1" and out[3:5] == ["alpha\t\t-1.0", "beta\t\t-2.0"]
+    assert out[6] == "Top ranked 2 terms for Topic 2" and out[8:10] == ["eps\t\t-5.5", "delta\t\t-6.0"]
+    gdir = tmp_path / "gamma-1"
+    gdir.mkdir()
+    seqfile.write_corpus(str(gdir / "gamma_gamma-m-00000"), [0, 1, 2], [1, 2], [3, 1], doc_id=[7, 9],
+                         gamma=np.array([[0.5, 1.25], [100.0, 1e-3]]), n_topics=2)
+    out = subprocess.run([tool, "document", "-input", str(gdir)], capture_output=True, text=True,
+                         check=True).stdout.splitlines()
+    assert out == ["7 0.5 1.25 ", "9 100.0 0.001 "]
