@@ -111,6 +111,14 @@ int mrlda_set_beta(mrlda_ctx *ctx, const double *digamma_lambda, const float *no
 /* The content of the next beta file (TermReducer output, TermReducer.java:173-195,232-235). */
 int mrlda_get_beta(mrlda_ctx *ctx, double *digamma_lambda, float *normaliser, uint8_t *present);
 
+/* -informedprior (InformedPrior.java:43-44,172-177; hook TermReducer.java:162-164): n (topic, term)
+ * pairs, both 1-based, name the seed terms of each topic.  With a prior set, the finalize uses
+ * log eta = (float)log(1000) for seed cells and (float)log(0.001) for all others instead of
+ * log(1e-12).  n = 0 removes the prior.  Deviation: the reference looks the seed set up under the
+ * previously reduced key's topic for the first term of each topic (TermReducer.java:164 runs before
+ * :188, and "previous" depends on -reducer); the topic itself is used here. */
+int mrlda_set_informed_prior(mrlda_ctx *ctx, int64_t n, const int32_t *topic, const int32_t *term);
+
 /* Direct injection / read-back of the K x V log-beta the mapper works with (term-major). */
 int mrlda_set_logbeta(mrlda_ctx *ctx, const double *logbeta);
 int mrlda_get_logbeta(mrlda_ctx *ctx, double *logbeta);

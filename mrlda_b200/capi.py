@@ -16,7 +16,7 @@ MRLDA_NCCL_ID_BYTES = 128
 EXPORTS = [
     "mrlda_default_config", "mrlda_create", "mrlda_destroy", "mrlda_last_error",
     "mrlda_set_corpus_csr", "mrlda_set_alpha", "mrlda_get_alpha", "mrlda_set_beta",
-    "mrlda_get_beta", "mrlda_set_logbeta", "mrlda_get_logbeta", "mrlda_init_beta_random",
+    "mrlda_get_beta", "mrlda_set_informed_prior", "mrlda_set_logbeta", "mrlda_get_logbeta", "mrlda_init_beta_random",
     "mrlda_iterate", "mrlda_e_step", "mrlda_m_step", "mrlda_get_gamma", "mrlda_get_alpha_ss",
     "mrlda_get_stats", "mrlda_update_vector_alpha", "mrlda_update_scalar_alpha",
     "mrlda_eval_special", "mrlda_measure_fp64_peak", "mrlda_debug_phase_cycles", "mrlda_nccl_unique_id", "mrlda_comm_init", "mrlda_kernel_launches",
@@ -83,6 +83,7 @@ def load():
     L.mrlda_get_alpha.argtypes = [_ctxp, _dp]
     L.mrlda_set_beta.argtypes = [_ctxp, _dp, _fp, _bp]
     L.mrlda_get_beta.argtypes = [_ctxp, _dp, _fp, _bp]
+    L.mrlda_set_informed_prior.argtypes = [_ctxp, C.c_int64, _ip, _ip]
     L.mrlda_set_logbeta.argtypes = [_ctxp, _dp]
     L.mrlda_get_logbeta.argtypes = [_ctxp, _dp]
     L.mrlda_init_beta_random.argtypes = [_ctxp]
@@ -225,6 +226,13 @@ class Context:
         self._ck(load().mrlda_get_beta(self._h, dl.ctypes.data_as(_dp), nm.ctypes.data_as(_fp),
                                        pr.ctypes.data_as(_bp)))
         return dl, nm, pr
+
+    def set_informed_prior(self, topics, terms):
+        """(topic, term) seed pairs, both 1-based; empty lists remove the prior."""
+        t = _arr(topics, np.int32)
+        v = _arr(terms, np.int32)
+        self._ck(load().mrlda_set_informed_prior(self._h, len(t), t.ctypes.data_as(_ip),
+                                                 v.ctypes.data_as(_ip)))
 
     def iterate(self):
         r = MrldaIterResult()

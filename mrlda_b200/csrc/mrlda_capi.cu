@@ -111,7 +111,17 @@ __global__ void expand_rows_kernel(const double *logbeta, double *E, double *row
 // K2a: per-slab partial column sums of lambda = eta + stats over the terms seen in the corpus
 // (the logNormalizeFactor fold of TermReducer.java:189,212, in linear space), and present[v].
 // A term was emitted by some mapper iff sum_k stats[v][k] = n_v > 0.
-__global__ void finalize_colsum_kernel(const double *stats, int V, int K, double eta, int slab,
+struct EtaSpec {  // eta per (term, topic) cell: uniform, or the informed prior's two levels
+  double eta, hi, lo;
+  const uint32_t *seed_bits;  // V*K bits, term-major; NULL = uniform eta
+  __device__ __forceinline__ double at(int v, int k, int K) const {
+    if (!seed_bits) return eta;
+    const size_t i = (size_t)v * K + k;
+    return (seed_bits[i >> 5] >> (i & 31)) & 1u ? hi : lo;
+  }
+};
+
+__global__ void finalize_colsum_kernel(const double *stats, int V, int K, EtaSpec eta, int slab,
                                        double *partial, uint8_t *present) {
   extern __shared__ double rs[];  // slab row sums
   int v0 = blockIdx.x * slab, v1 = min(V, v0 + slab);
@@ -130,7 +140,7 @@ __global__ void finalize_colsum_kernel(const double *stats, int V, int K, double
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     double acc = 0.0;
     for (int v = v0; v < v1; v++)
-      if (rs[v - v0] > 0.0) acc += eta + stats[(size_t)v * K + k];
+      if (rs[v - v0] > 0.0) acc += eta.at(v, k, K) + stats[(size_t)v * K + k];
     partial[(size_t)blockIdx.x * K + k] = acc;
   }
 }
@@ -149,7 +159,7 @@ __global__ void finalize_norm_kernel(const double *partial, int nslabs, int K, f
 // K2c: per term row: digamma(lambda) (the beta file value, TermReducer.java:195,213), the
 // importBeta subtraction (DocumentMapper.java:511), row max and E.  One warp per term.
 __global__ void finalize_rows_kernel(const double *stats, const uint8_t *present, const float *nrm,
-                                     double eta, int V, int K, int KS, double *dl, double *logbeta,
+                                     EtaSpec eta, int V, int K, int KS, double *dl, double *logbeta,
                                      double *E, double *rowmax) {
   int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (warp >= V) return;
@@ -158,7 +168,7 @@ __global__ void finalize_rows_kernel(const double *stats, const uint8_t *present
   double *dlr = dl + (size_t)warp * K, *lbr = logbeta + (size_t)warp * K;
   double mx = -INFINITY;
   for (int k = lane; k < K; k += 32) {
-    double lam = eta + row[k];
+    double lam = eta.at(warp, k, K) + row[k];
     double v = digamma_literal(lam);
     dlr[k] = v;
     double lb = v - (double)nrm[k];
@@ -430,6 +440,7 @@ struct mrlda_ctx {
   float *d_nrm = nullptr;
   uint8_t *d_present = nullptr;
   bool alpha_set = false, beta_set = false, have_dl = false;
+  uint32_t *d_seed_bits = nullptr;  // informed prior (NULL: uniform eta)
 
   // per-iteration
   double *d_alpha_ss = nullptr;   // K
@@ -546,7 +557,7 @@ void mrlda_destroy(mrlda_ctx *ctx) {
                   ctx->d_gamma,   ctx->d_alpha,  ctx->d_lik_alpha, ctx->d_logbeta, ctx->d_E,
                   ctx->d_rowmax,  ctx->d_dl,     ctx->d_stats,    ctx->d_nrm,    ctx->d_present,
                   ctx->d_alpha_ss, ctx->d_counters, ctx->d_work,  ctx->d_partial, ctx->d_colsum,
-                  ctx->d_alpha_work, ctx->d_phase};
+                  ctx->d_alpha_work, ctx->d_phase, ctx->d_seed_bits};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &e : ctx->ev)
@@ -905,6 +916,31 @@ int mrlda_get_beta(mrlda_ctx *ctx, double *digamma_lambda, float *normaliser, ui
   return MRLDA_OK;
 }
 
+int mrlda_set_informed_prior(mrlda_ctx *ctx, int64_t n, const int32_t *topic, const int32_t *term) {
+  if (!ctx || n < 0 || (n > 0 && (!topic || !term))) return MRLDA_EINVAL;
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (n == 0) {
+    if (ctx->d_seed_bits) cudaFree(ctx->d_seed_bits);
+    ctx->d_seed_bits = nullptr;
+    return MRLDA_OK;
+  }
+  const size_t words = ((size_t)ctx->V * ctx->K + 31) / 32;
+  std::vector<uint32_t> bits(words, 0u);
+  for (int64_t i = 0; i < n; i++) {
+    if (topic[i] < 1 || topic[i] > ctx->K || term[i] < 1 || term[i] > ctx->V) {
+      set_err(ctx, "mrlda_set_informed_prior: (topic %d, term %d) out of range", topic[i], term[i]);
+      return MRLDA_EINVAL;
+    }
+    const size_t at = (size_t)(term[i] - 1) * ctx->K + (size_t)(topic[i] - 1);
+    bits[at >> 5] |= 1u << (at & 31);
+  }
+  if (!ctx->d_seed_bits) CK(cudaMalloc(&ctx->d_seed_bits, words * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(ctx->d_seed_bits, bits.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return MRLDA_OK;
+}
+
 int mrlda_get_gamma(mrlda_ctx *ctx, double *gamma) {
   if (!ctx || !gamma) return MRLDA_EINVAL;
   if (!ctx->d_gamma) {
@@ -1149,15 +1185,21 @@ int mrlda_m_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   const int K = ctx->K, V = ctx->V;
   int launches0 = (int)ctx->launches;
   CK(cudaEventRecord(ctx->ev[4], st));
+  EtaSpec eta;
+  eta.eta = ctx->cfg.eta;
+  // InformedPrior.java:43-44: the log etas are floats; the reducer exponentiates the promoted value
+  eta.hi = exp((double)(float)log(1000.0));
+  eta.lo = exp((double)(float)log(0.001));
+  eta.seed_bits = ctx->d_seed_bits;
   finalize_colsum_kernel<<<ctx->nslabs, 256, ctx->slab * sizeof(double), st>>>(
-      ctx->d_stats, V, K, ctx->cfg.eta, ctx->slab, ctx->d_partial, ctx->d_present);
+      ctx->d_stats, V, K, eta, ctx->slab, ctx->d_partial, ctx->d_present);
   finalize_norm_kernel<<<(K + 127) / 128, 128, 0, st>>>(ctx->d_partial, ctx->nslabs, K, ctx->d_nrm,
                                                         ctx->d_colsum);
   {
     int threads = 256;
     int64_t blocks = ((int64_t)V * 32 + threads - 1) / threads;
     finalize_rows_kernel<<<(unsigned)blocks, threads, 0, st>>>(ctx->d_stats, ctx->d_present,
-                                                                ctx->d_nrm, ctx->cfg.eta, V, K,
+                                                                ctx->d_nrm, eta, V, K,
                                                                 ctx->ES, ctx->d_dl, ctx->d_logbeta,
                                                                 ctx->d_E, ctx->d_rowmax);
   }

@@ -194,6 +194,36 @@ inline void write_gamma(const std::string &file, const Corpus &c, int64_t lo, in
   }
 }
 
+// The eta file of -informedprior: SequenceFile<IntWritable topic (1-based), ArrayListOfIntsWritable
+// seed term ids> as written by InformedPrior.exportTerms (InformedPrior.java:139-170) and read by
+// importEta (:179-202).  ArrayListOfIntsWritable = int32 size, then size int32 values.
+static const char *const kArrayListOfInts = "edu.umd.cloud9.io.array.ArrayListOfIntsWritable";
+inline void read_eta(const std::string &path, std::vector<int32_t> &topic, std::vector<int32_t> &term) {
+  SeqReader r(path);
+  const uint8_t *k, *v;
+  size_t kl, vl;
+  while (r.next(k, kl, v, vl)) {
+    ByteReader kr(k, kl), vr(v, vl);
+    int32_t t = kr.i32();
+    if (t <= 0) throw std::invalid_argument("Invalid eta prior for term " + std::to_string(t) + "...");
+    int32_t n = vr.i32();
+    for (int32_t i = 0; i < n; i++) {
+      topic.push_back(t);
+      term.push_back(vr.i32());
+    }
+  }
+}
+inline void write_eta(const std::string &path, const std::vector<std::vector<int32_t>> &seeds) {
+  SeqWriter w(path, kIntWritable, kArrayListOfInts);
+  for (size_t t = 0; t < seeds.size(); t++) {
+    ByteWriter k, v;
+    k.i32((int32_t)t + 1);
+    v.i32((int32_t)seeds[t].size());
+    for (int32_t x : seeds[t]) v.i32(x);
+    w.append(k, v);
+  }
+}
+
 // java.lang.Double.toString: shortest digits that round-trip; decimal notation for
 // 1e-3 <= |d| < 1e7, otherwise computerised scientific notation.
 inline std::string java_double(double d) {

@@ -43,6 +43,7 @@ void info(const std::string &s) { printf("INFO  VariationalInference: %s\n", s.c
           "usage: cc.mrlda.VariationalInference\n"
           " -directemit            disable in-mapper-combiner (accepted; statistics always sum over all documents)\n"
           " -help                  print the help message\n"
+          " -informedprior <path>  seed informed prior (eta file written by cc.mrlda.InformedPrior)\n"
           " -input <path>          input file or directory\n"
           " -iteration <int>       number of iterations (default - 30)\n"
           " -mapper <int>          number of mappers (accepted, ignored)\n"
@@ -125,7 +126,7 @@ Options parse(int argc, char **argv) {
   check(o.terms > 0, "Illegal settings for term option: must be strictly positive...");
   if (!o.training) o.random_start = false;  // "ignored in testing mode" (VIO.java:216-223)
   check(o.mappers > 0, "Illegal settings for mapper option: must be strictly positive...");
-  check(o.informed_prior.empty(), "-informedprior is outside the scope of this build (SURVEY.md 8f-4)");
+  if (!o.training) o.informed_prior.clear();  // "ignored in test mode" (VIO.java:226-233)
   check(o.world >= 1 && o.rank >= 0 && o.rank < o.world, "bad -rank/-world");
   return o;
 }
@@ -214,6 +215,26 @@ int main(int argc, char **argv) {
     cfg.seed = o.seed;
     mrlda_ctx *ctx = nullptr;
     if (mrlda_create(&cfg, &ctx) != MRLDA_OK) die(nullptr, "mrlda_create");
+
+    if (!o.informed_prior.empty()) {  // VariationalInference.java:118-124,198-201
+      check(exists(o.informed_prior) && !is_dir(o.informed_prior),
+            "Illegal informed prior file: must be an existing file...");
+      std::vector<int32_t> topic, term;
+      read_eta(o.informed_prior, topic, term);
+      if (o.rank == 0) {  // the reference copies the file to <output>eta
+        FILE *src = fopen(o.informed_prior.c_str(), "rb"), *dst = fopen((o.output + "eta").c_str(), "wb");
+        if (src && dst) {
+          char buf[1 << 16];
+          size_t got;
+          while ((got = fread(buf, 1, sizeof buf, src)) > 0) fwrite(buf, 1, got, dst);
+        }
+        if (src) fclose(src);
+        if (dst) fclose(dst);
+      }
+      if (mrlda_set_informed_prior(ctx, (int64_t)topic.size(), topic.data(), term.data()) != MRLDA_OK)
+        die(ctx, "mrlda_set_informed_prior");
+      info(" - informed prior: " + o.informed_prior + " (" + std::to_string(topic.size()) + " seed terms)");
+    }
 
     if (o.world > 1) {  // one process per GPU: rank 0 publishes the NCCL id through a file
       check(!o.nccl_id_file.empty(), "-ncclid <file> is required with -world > 1");

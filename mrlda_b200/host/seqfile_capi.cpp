@@ -106,6 +106,12 @@ int mrlda_io_write_term_index(const char *path, int32_t n, const char *terms_nl)
           ByteWriter k, v; k.i32(i); v.text(t); w.append(k, v); p = e ? e + 1 : p + t.size();
         } return 0;)
 }
+// eta file of -informedprior: n (topic, term) pairs, topics 1..k
+int mrlda_io_write_eta(const char *path, int32_t k, int64_t n, const int32_t *topic, const int32_t *term) {
+  GUARD(std::vector<std::vector<int32_t>> seeds((size_t)k);
+        for (int64_t i = 0; i < n; i++) seeds.at((size_t)topic[i] - 1).push_back(term[i]);
+        write_eta(path, seeds); return 0;)
+}
 // java.lang.Double.toString, for the likelihood log lines
 int mrlda_io_java_double(double d, char *out, int32_t cap) {
   std::string s = java_double(d);

@@ -40,6 +40,7 @@ def load():
         L.mrlda_io_read_beta.argtypes = [C.c_char_p, C.c_int32, C.c_int32, _dp, _fp, _bp]
         L.mrlda_io_java_double.argtypes = [C.c_double, C.c_char_p, C.c_int32]
         L.mrlda_io_write_term_index.argtypes = [C.c_char_p, C.c_int32, C.c_char_p]
+        L.mrlda_io_write_eta.argtypes = [C.c_char_p, C.c_int32, C.c_int64, _ip, _ip]
         _lib = L
     return _lib
 
@@ -152,3 +153,11 @@ def java_double(x):
 def write_term_index(path, terms):
     """ParseCorpus's term index: SequenceFile<IntWritable, Text>, ids 1..len(terms)."""
     _ck(load().mrlda_io_write_term_index(os.fsencode(path), len(terms), "\n".join(terms).encode()))
+
+
+def write_eta(path, n_topics, topics, terms):
+    """The -informedprior file: SequenceFile<IntWritable topic, ArrayListOfIntsWritable seed terms>."""
+    t = np.ascontiguousarray(topics, dtype=np.int32)
+    v = np.ascontiguousarray(terms, dtype=np.int32)
+    _ck(load().mrlda_io_write_eta(os.fsencode(path), n_topics, len(t), t.ctypes.data_as(_ip),
+                                  v.ctypes.data_as(_ip)))

@@ -254,7 +254,7 @@ int64_t mrlda_oracle_estep(int K, int sweeps, int64_t D, const int64_t *row_ptr,
  */
 int64_t mrlda_oracle_mstep(int K, int V, int64_t D, const int64_t *row_ptr, const int32_t *term_id,
                            const double *log_phi, double *digamma_lambda, float *normaliser,
-                           uint8_t *present) {
+                           uint8_t *present, const uint8_t *seed) {
   int64_t Z = row_ptr[D];
   size_t cells = (size_t)V * (size_t)K;
   double *acc = (double *)malloc(sizeof(double) * cells);
@@ -271,6 +271,11 @@ int64_t mrlda_oracle_mstep(int K, int V, int64_t D, const int64_t *row_ptr, cons
     }
   }
   double log_eta = log(MRLDA_ETA);
+  /* -informedprior (InformedPrior.java:43-44,172-177; hook TermReducer.java:162-164): seed[v*K+k]
+   * says term v+1 is a seed of topic k+1; log eta is a FLOAT, log 1000 for seeds, log 0.001 else.
+   * Deviation: the reference looks the seed set up under the previously reduced key's topic for the
+   * first term of every topic (TermReducer.java:164 runs before :188); the topic itself is used. */
+  const double log_eta_hi = (double)(float)log(1000.0), log_eta_lo = (double)(float)log(0.001);
   int64_t seen = 0;
   for (int v = 0; v < V; v++) seen += present[v] ? 1 : 0;
 #pragma omp parallel for schedule(static)
@@ -279,7 +284,8 @@ int64_t mrlda_oracle_mstep(int K, int V, int64_t D, const int64_t *row_ptr, cons
     double lnnorm = 0;
     for (int v = 0; v < V; v++) {
       if (!present[v]) continue;
-      double lnlam = mrlda_oracle_logadd(log_eta, acc[(size_t)v * K + k]);
+      double le = seed ? (seed[(size_t)v * K + k] ? log_eta_hi : log_eta_lo) : log_eta;
+      double lnlam = mrlda_oracle_logadd(le, acc[(size_t)v * K + k]);
       digamma_lambda[(size_t)v * K + k] = mrlda_oracle_digamma(exp(lnlam));
       if (first) {
         lnnorm = lnlam;
@@ -432,14 +438,14 @@ int64_t mrlda_oracle_iterate(int K, int V, int sweeps, int64_t D, const int64_t 
                              const double *alpha, int has_gamma, int random_start, int learning,
                              int symmetric, double *gamma, double *digamma_lambda,
                              float *normaliser, uint8_t *present, double *alpha_out,
-                             double *alpha_ss, int64_t *n_terms_seen) {
+                             double *alpha_ss, int64_t *n_terms_seen, const uint8_t *seed) {
   int64_t Z = row_ptr[D];
   double *log_phi = learning ? (double *)malloc(sizeof(double) * (size_t)Z * K) : NULL;
   int64_t counter = mrlda_oracle_estep(K, sweeps, D, row_ptr, term_id, count, logbeta, alpha,
                                        has_gamma, random_start, gamma, log_phi, alpha_ss, NULL);
   if (learning) {
     int64_t seen =
-        mrlda_oracle_mstep(K, V, D, row_ptr, term_id, log_phi, digamma_lambda, normaliser, present);
+        mrlda_oracle_mstep(K, V, D, row_ptr, term_id, log_phi, digamma_lambda, normaliser, present, seed);
     if (n_terms_seen) *n_terms_seen = seen;
     mrlda_oracle_update_alpha(K, (int)D, symmetric, alpha, alpha_ss, alpha_out);
     free(log_phi);

@@ -53,12 +53,12 @@ def lib():
         L.mrlda_oracle_estep.argtypes = [C.c_int, C.c_int, C.c_int64, _lp, _ip, _ip, _dp, _dp,
                                          C.c_int, C.c_int, _dp, _dp, _dp, _lp]
         L.mrlda_oracle_mstep.restype = C.c_int64
-        L.mrlda_oracle_mstep.argtypes = [C.c_int, C.c_int, C.c_int64, _lp, _ip, _dp, _dp, _fp, _bp]
+        L.mrlda_oracle_mstep.argtypes = [C.c_int, C.c_int, C.c_int64, _lp, _ip, _dp, _dp, _fp, _bp, _bp]
         L.mrlda_oracle_import_beta.argtypes = [C.c_int, C.c_int, _dp, _fp, _bp, _dp]
         L.mrlda_oracle_iterate.restype = C.c_int64
         L.mrlda_oracle_iterate.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, _lp, _ip, _ip, _dp,
                                            _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _fp,
-                                           _bp, _dp, _dp, _lp]
+                                           _bp, _dp, _dp, _lp, _bp]
         L.mrlda_oracle_converged.restype = C.c_int
         L.mrlda_oracle_converged.argtypes = [C.c_double, C.c_double]
         _lib = L
@@ -146,7 +146,7 @@ def import_beta(K, V, digamma_lambda, normaliser, present):
 
 
 def iterate(K, V, row_ptr, term_id, count, logbeta, alpha, gamma=None, random_start=False,
-            learning=True, symmetric=False, sweeps=99):
+            learning=True, symmetric=False, sweeps=99, seed=None):
     """One EM iteration.  Returns dict(counter, log_likelihood, gamma, digamma_lambda, normaliser,
     present, alpha, alpha_ss, n_terms_seen, logbeta) with logbeta = importBeta(new beta)."""
     row_ptr = np.ascontiguousarray(row_ptr, dtype=np.int64)
@@ -164,11 +164,12 @@ def iterate(K, V, row_ptr, term_id, count, logbeta, alpha, gamma=None, random_st
     a_out = alpha.copy()
     ss = np.zeros(K, dtype=np.float64)
     seen = C.c_int64(0)
+    sd = np.ascontiguousarray(seed, dtype=np.uint8) if seed is not None else None
     counter = lib().mrlda_oracle_iterate(K, V, sweeps, D, _p(row_ptr, _lp), _p(term_id, _ip),
                                          _p(count, _ip), _p(logbeta, _dp), _p(alpha, _dp),
                                          int(has_gamma), int(random_start), int(learning),
                                          int(symmetric), _p(g, _dp), _p(dl, _dp), _p(nm, _fp),
-                                         _p(pr, _bp), _p(a_out, _dp), _p(ss, _dp), C.byref(seen))
+                                         _p(pr, _bp), _p(a_out, _dp), _p(ss, _dp), C.byref(seen), _p(sd, _bp))
     res = dict(counter=int(counter), log_likelihood=-int(counter) / 1e6, gamma=g.reshape(D, K),
                alpha_ss=ss, alpha=a_out, n_terms_seen=int(seen.value))
     if learning:

@@ -102,6 +102,29 @@ def test_fresh_training_then_test_mode(tmp_path, oracle):
     assert not any(f.startswith(("alpha-", "beta-")) for f in os.listdir(tout))  # no model written
 
 
+def test_informed_prior_option(tmp_path, oracle):
+    K, V = 6, 150
+    c = corpus.generate(80, V, K, 30, seed=8)
+    out = str(tmp_path / "m") + "/"
+    os.makedirs(out + "gamma-1")
+    alpha1, lb1 = np.full(K, 0.1), corpus.init_logbeta(V, K, seed=9)
+    seqfile.write_alpha(out + "alpha-1", alpha1)
+    seqfile.write_beta(out + "beta-1", lb1, np.zeros(K, dtype=np.float32), np.ones(V, dtype=np.uint8))
+    seqfile.write_corpus(out + "gamma-1/gamma_gamma-m-00000", c.row_ptr, c.term_id, c.count)
+    topics, terms = np.array([1, 1, 2, 6]), np.array([3, 7, 9, 150])
+    eta = str(tmp_path / "eta-in")
+    seqfile.write_eta(eta, K, topics, terms)
+    log = run_driver("-input", "x", "-output", out, "-term", V, "-topic", K, "-iteration", 2,
+                     "-modelindex", 1, "-informedprior", eta)
+    assert "4 seed terms" in log and os.path.exists(out + "eta")
+    seed = np.zeros((V, K), dtype=np.uint8)
+    seed[terms - 1, topics - 1] = 1
+    ref = oracle.iterate(K, V, c.row_ptr, c.term_id, c.count, lb1, alpha1, seed=seed)
+    dl, nm, pr = seqfile.read_beta(out + "beta-2", K, V)
+    s = ref["present"].astype(bool)
+    assert np.array_equal(nm, ref["normaliser"]) and rel_err(dl[s], ref["digamma_lambda"][s]) < 1e-9
+
+
 def test_option_errors_print_help_and_exit_zero():
     """The reference logs the parse error, prints the usage and exits 0 (VIO.java:251-266)."""
     for args in (["-output", "x", "-term", "5", "-topic", "2"],                      # -input missing

@@ -230,6 +230,45 @@ def test_three_em_iterations_track_oracle(capi, oracle, kernel_mode):
             lb_ref = np.where(seen[:, None], ref["logbeta"], lb_ref)
 
 
+def test_informed_prior_changes_eta_per_cell(capi, oracle):
+    """-informedprior: log eta = (float)log 1000 for seed (topic, term) cells, (float)log 0.001 for
+    the others (InformedPrior.java:43-44,172-177; TermReducer.java:162-164)."""
+    from mrlda_b200 import corpus
+    K = 8
+    c = small_corpus(D=60, V=120, K=K, seed=31)
+    alpha = np.full(K, 0.05)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=6)
+    rng = np.random.default_rng(2)
+    topics = rng.integers(1, K + 1, size=40)
+    terms = rng.integers(1, c.n_terms + 1, size=40)
+    seed = np.zeros((c.n_terms, K), dtype=np.uint8)
+    seed[terms - 1, topics - 1] = 1
+    ref = oracle.iterate(K, c.n_terms, c.row_ptr, c.term_id, c.count, lb, alpha, seed=seed)
+    plain = oracle.iterate(K, c.n_terms, c.row_ptr, c.term_id, c.count, lb, alpha)
+    with capi.Context(K, c.n_terms) as ctx:
+        ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count)
+        ctx.set_alpha(alpha)
+        ctx.set_logbeta(lb)
+        ctx.set_informed_prior(topics, terms)
+        ctx.iterate()
+        dl, nm, pr = ctx.get_beta()
+        got_lb = ctx.get_logbeta()
+        with pytest.raises(capi.MrldaError):
+            ctx.set_informed_prior([K + 1], [1])
+        ctx.set_informed_prior([], [])  # removes the prior again
+        ctx.set_logbeta(lb)
+        ctx.set_alpha(alpha)
+        ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count)
+        ctx.iterate()
+        dl0, nm0, _ = ctx.get_beta()
+    seen = ref["present"].astype(bool)
+    assert np.array_equal(nm, ref["normaliser"]) and np.array_equal(nm0, plain["normaliser"])
+    assert rel_err(dl[seen], ref["digamma_lambda"][seen]) < TOL
+    assert rel_err(got_lb[seen], ref["logbeta"][seen]) < TOL
+    assert rel_err(dl0[seen], plain["digamma_lambda"][seen]) < TOL
+    assert rel_err(dl[seen], plain["digamma_lambda"][seen]) > 1e-3  # the prior really acted
+
+
 def test_alpha_known_answers_on_device(capi):
     """The reference's own KATs (VariationalInferenceTest.java:27-62) through the device kernels."""
     with capi.Context(3, 10) as ctx:
