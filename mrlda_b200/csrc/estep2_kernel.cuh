@@ -19,12 +19,18 @@
 //     transposed through shared memory (or reduce-scattered in registers) so that S_c lands in the
 //     lane that owns column c, which updates gamma_c.  gamma, alpha and the alpha sufficient
 //     statistics stay in the owner lane's registers.
+//   * CL > 1: a thread-block cluster of CL CTAs (one per SM) owns the document; the topic split
+//     continues across the CTAs (CTA r, warp w owns columns [(r*NW+w)*CPW, +CPW)), so K up to
+//     CL*NW*CPW = 1024 fits on chip.  The only cross-CTA traffic is the per-row partial dot products,
+//     read through distributed shared memory after one cluster barrier per sweep.
 //   * WPS = warps per SM the variant is compiled for: 8 (255 registers per thread, most of the tile
 //     in registers) or 16 (128 registers per thread, more of the tile in shared memory, twice the
 //     warps to hide the FP64 / shared-memory latencies of the serial phases).
 //   * Work is perfectly balanced across warps (every warp walks all rows); the only idle lanes are
 //     those of the last, partially filled slot.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "estep_kernel.cuh"
 #include "tmem_ops.cuh"
 
@@ -75,13 +81,16 @@ __host__ __device__ constexpr size_t estep2_smem_bytes(int rsm, int cap_rows) {
                            + 96);                        // reductions + doc meta
 }
 
-template <int NW, int CPW, int RREG, bool LAST>
+template <int NW, int CPW, int RREG, int CL, bool LAST>
 __device__ __forceinline__ void estep2_sweep(
     const EstepArgs &a, double (&e)[RREG][CPW], const double *es, double *part, const double *cnt_s,
     double *r_s, int *flag_s, const double *theta_w, double (&s)[CPW], double &lik,
     unsigned &badbits, const int64_t b, const int n, const int nslots, const int cap_rows,
-    const int warp, const int lane, long long *tm, const uint32_t tbase, const int rt) {
+    const int warp, const int lane, long long *tm, const uint32_t tbase, const int rt,
+    const int crank) {
   (void)tm;
+  namespace cg = cooperative_groups;
+  const int gwarp = crank * NW + warp;  // position of my warp's column slice among all CL*NW slices
   constexpr int HALF = CPW / 2, TS = estep2_tmem_stride(CPW);
   // slot q lives in registers (q < RREG), in TMEM (q < RREG + rt) or in shared memory
   const int nt_end = nslots < RREG + rt ? nslots : RREG + rt;
@@ -148,23 +157,52 @@ __device__ __forceinline__ void estep2_sweep(
     }
   }
   MRLDA_TICK(2);
-  __syncthreads();  // B1: partial dots published
-  MRLDA_TICK(3);
-
-  // (3a) one thread per row: norm_w = sum of the NW partials, r_w = n_w / norm_w; a row whose norm
-  // underflowed is flagged with r = -1 and redone exactly in log space by the caller
-  {
-    const int nrows = 32 * (nslots > RREG ? nslots : RREG);
+  const int nrows = 32 * (nslots > RREG ? nslots : RREG);
+  if constexpr (CL > 1) {
+    // distributed shared memory is slow (~20 B/clk): fold the NW partials of every row locally
+    // first, so that each CTA reads one value per row and peer instead of NW
+    __syncthreads();
     for (int row = warp * 32 + lane; row < nrows; row += NW * 32) {
-      const double *pp = part + row;
-      double n0 = pp[0], n1 = 0.0, n2 = 0.0, n3 = 0.0;
+      double *pp = part + row;
+      double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
 #pragma unroll
-      for (int w2 = 1; w2 < NW; w2++) {
+      for (int w2 = 0; w2 < NW; w2++) {
         const double v = pp[(size_t)w2 * cap_rows];
         if ((w2 & 3) == 0) n0 += v;
         else if ((w2 & 3) == 1) n1 += v;
         else if ((w2 & 3) == 2) n2 += v;
         else n3 += v;
+      }
+      pp[0] = (n0 + n1) + (n2 + n3);  // only this thread touches the partials of this row
+    }
+    cg::this_cluster().sync();  // B1 across the cluster: every CTA's row partials published
+  } else {
+    __syncthreads();  // B1: partial dots published
+  }
+  MRLDA_TICK(3);
+
+  // (3a) one thread per row: norm_w = sum of the partials, r_w = n_w / norm_w; a row whose norm
+  // underflowed is flagged with r = -1 and redone exactly in log space by the caller
+  {
+    for (int row = warp * 32 + lane; row < nrows; row += NW * 32) {
+      double n0 = 0.0, n1 = 0.0, n2 = 0.0, n3 = 0.0;
+      if constexpr (CL > 1) {
+#pragma unroll
+        for (int r = 0; r < CL; r++) {  // fixed order: every CTA of the cluster gets the same bits
+          const double v = cg::this_cluster().map_shared_rank(part, r)[row];
+          if (r & 1) n1 += v;
+          else n0 += v;
+        }
+      } else {
+        const double *pp = part + row;
+#pragma unroll
+        for (int w2 = 0; w2 < NW; w2++) {
+          const double v = pp[(size_t)w2 * cap_rows];
+          if ((w2 & 3) == 0) n0 += v;
+          else if ((w2 & 3) == 1) n1 += v;
+          else if ((w2 & 3) == 2) n2 += v;
+          else n3 += v;
+        }
       }
       const double norm = (n0 + n1) + (n2 + n3);
       const bool valid = row < n;
@@ -173,7 +211,7 @@ __device__ __forceinline__ void estep2_sweep(
       const double cn = cnt_s[row];
       r_s[row] = bad ? -1.0 : (ok ? cn : 0.0) * rcp_fast(ok ? norm : 1.0);
       if (bad) *flag_s = 1;
-      if (LAST && ok)  // likelihoodPhi, first part (DocumentMapper.java:421 summed over topics)
+      if (LAST && ok && crank == 0)  // likelihoodPhi, first part (DocumentMapper.java:421 summed over topics)
         lik = fma(cn, log(norm) + __ldg(a.rowmax + __ldg(a.term_id + b + row) - 1), lik);
     }
   }
@@ -189,10 +227,10 @@ __device__ __forceinline__ void estep2_sweep(
     // statistics scatter of the last sweep: n_w phi_wk = r_w theta_k E_wk (DocumentMapper.java:315-329)
     if (!(r > 0.0) || !a.learning) return;
     const int term = __ldg(a.term_id + b + 32 * q + lane);
-    double *srow = a.stats + (size_t)(term - 1) * K + warp * CPW;
+    double *srow = a.stats + (size_t)(term - 1) * K + gwarp * CPW;
 #pragma unroll
     for (int c = 0; c < CPW; c++)
-      if (warp * CPW + c < K) atomicAdd(srow + c, r * theta_w[c] * erow[c]);
+      if (gwarp * CPW + c < K) atomicAdd(srow + c, r * theta_w[c] * erow[c]);
   };
   {
     double r[RREG];
@@ -262,9 +300,12 @@ __device__ __forceinline__ void estep2_sweep(
   }
 }
 
-template <int NW, int CPW, int RREG, int WPS>
+template <int NW, int CPW, int RREG, int WPS, int CL>
 __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepArgs a) {
-  constexpr int HALF = CPW / 2, KS = NW * CPW;
+  namespace cg = cooperative_groups;
+  constexpr int HALF = CPW / 2, KS = NW * CPW;  // KS: columns of this CTA
+  int crank = 0;
+  if constexpr (CL > 1) crank = (int)cg::this_cluster().block_rank();
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -313,7 +354,9 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       if (c2 == lane) rs_src = l2;
     }
   }
-  const int col = warp * CPW + mycol;
+  const int gwarp = crank * NW + warp;
+  const int lcol = warp * CPW + mycol;   // column index inside this CTA
+  const int col = gwarp * CPW + mycol;   // topic
   const bool owner = mycol >= 0 && col < K;
   const double alpha_c = owner ? a.alpha[col] : 1.0;
   double ss_acc = 0.0;  // my column's alpha sufficient statistic over all my documents
@@ -326,11 +369,18 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
   if (tid == 0) meta_s[1] = 0;
   double *theta_w = theta_s + warp * CPW;
 
+  int round = 0;
   for (;;) {
     __syncthreads();
-    if (tid == 0) meta_s[0] = a.doc_begin + atomicAdd(a.work_counter, 1);
-    __syncthreads();
-    const int qi = meta_s[0];
+    int qi;
+    if constexpr (CL == 1) {
+      if (tid == 0) meta_s[0] = a.doc_begin + atomicAdd(a.work_counter, 1);
+      __syncthreads();
+      qi = meta_s[0];
+    } else {  // all CTAs of a cluster must agree on the document: static round-robin over clusters
+      qi = a.doc_begin + (int)(blockIdx.x / CL) + round * (int)(gridDim.x / CL);
+      round++;
+    }
     if (qi >= a.doc_end) break;
     const int d = a.doc_order[qi];
     const int64_t b = a.row_ptr[d];
@@ -345,7 +395,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       const int row = 32 * q + lane;
       if (row < n) {
         const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW);
 #pragma unroll
         for (int i = 0; i < HALF; i++) {
           double2 v = __ldg(src + i);
@@ -365,7 +415,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       for (int i = 0; i < TS; i++) w32[i] = 0u;
       if (row < n) {
         const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW);
 #pragma unroll
         for (int i = 0; i < HALF; i++) {
           const double2 v = __ldg(src + i);
@@ -384,7 +434,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
                      ((size_t)((q - RREG - rt) * NW + warp) * HALF) * 32 + lane;
       if (row < n) {
         const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW);
 #pragma unroll
         for (int i = 0; i < HALF; i++) dst[(size_t)i * 32] = __ldg(src + i);
       } else {
@@ -421,11 +471,11 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       MRLDA_TICK(1);
       double *part = part_s + (size_t)(sweep & 1) * NW * cap_rows;
       if (!last)
-        estep2_sweep<NW, CPW, RREG, false>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
-                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt);
+        estep2_sweep<NW, CPW, RREG, CL, false>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
+                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank);
       else
-        estep2_sweep<NW, CPW, RREG, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
-                                          badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt);
+        estep2_sweep<NW, CPW, RREG, CL, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
+                                          badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank);
       MRLDA_TICK(6);
       // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
       // document leaves it free, else reduce-scatter in registers
@@ -466,10 +516,22 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       // warp computed the same norms)
       const bool anybad = meta_s[1] != 0;  // written before B2 by the row threads: CTA-uniform
       if (anybad) {
-        if (owner) gam_s[col] = gam;
-        __syncthreads();
+        auto csync = [&]() {
+          if constexpr (CL > 1)
+            cg::this_cluster().sync();
+          else
+            __syncthreads();
+        };
+        if (mycol >= 0) gam_s[lcol] = owner ? gam : 1.0;
+        csync();
         if (tid == 0) meta_s[1] = 0;
         if (warp == 0) {
+          auto gamma_of = [&](int k) -> double {  // gamma_k lives in the CTA that owns topic k
+            if constexpr (CL > 1)
+              return cg::this_cluster().map_shared_rank(gam_s, k / KS)[k % KS];
+            else
+              return gam_s[k];
+          };
           for (int q = 0; q < nslots; q++) {
             unsigned m = __ballot_sync(0xffffffffu, (badbits >> q) & 1u);
             while (m) {
@@ -480,35 +542,36 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
               const double nw_ = (double)__ldg(a.count + z);
               const double *lb = a.logbeta + (size_t)(term - 1) * K;
               double mx = -INFINITY;
-              for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gam_s[k]));
+              for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gamma_of(k)));
               mx = warp_max(mx);
               double sum = 0.0;
-              for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gam_s[k]) - mx);
+              for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gamma_of(k)) - mx);
               sum = warp_sum(sum);
               const double lsum = log(sum);
               for (int k = lane; k < K; k += 32) {
-                double lphi = lb[k] + digamma_fast(gam_s[k]) - mx - lsum;
+                if (k / KS != crank) continue;  // contributions go to the CTA that owns topic k
+                double lphi = lb[k] + digamma_fast(gamma_of(k)) - mx - lsum;
                 double c = nw_ * exp(lphi);
                 if (c > 0.0) {
-                  gextra_s[k] += c;  // one warp, distinct k per lane: no race
+                  gextra_s[k - crank * KS] += c;  // one warp, distinct k per lane: no race
                   if (last) {
                     lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
                     if (a.learning) atomicAdd(a.stats + (size_t)(term - 1) * K + k, c);
                   }
                 }
               }
-              if (lane == 0) atomicAdd(a.slow_rows, 1);
+              if (lane == 0 && crank == 0) atomicAdd(a.slow_rows, 1);
             }
           }
         }
-        __syncthreads();
+        csync();
       }
       if (!last) {
         if (owner) {
           double gnew = fma(theta_c, S_c, alpha_c);  // DocumentMapper.java:232-234
           if (anybad) {
-            gnew += gextra_s[col];
-            gextra_s[col] = 0.0;
+            gnew += gextra_s[lcol];
+            gextra_s[lcol] = 0.0;
           }
           gam = gnew;
         }
@@ -519,8 +582,8 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
           const double add = theta_c * S_c;
           g_new = alpha_c + add;
           if (anybad) {
-            g_new += gextra_s[col];
-            gextra_s[col] = 0.0;
+            g_new += gextra_s[lcol];
+            gextra_s[lcol] = 0.0;
           }
           if (add != 0.0) lik -= digamma_fast(gam) * add;
           lg = lgamma(g_new);
@@ -534,17 +597,28 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
           red_s[16 + warp] = lg;
           red_s[32 + warp] = lik;
         }
-        __syncthreads();
+        if constexpr (CL > 1)
+          cg::this_cluster().sync();
+        else
+          __syncthreads();
         double tg = 0.0, tl = 0.0, tk = 0.0;
 #pragma unroll
-        for (int w2 = 0; w2 < NW; w2++) {
-          tg += red_s[w2];
-          tl += red_s[16 + w2];
-          tk += red_s[32 + w2];
+        for (int r = 0; r < CL; r++) {
+          const double *rp = red_s;
+          if constexpr (CL > 1) rp = cg::this_cluster().map_shared_rank(red_s, r);
+#pragma unroll
+          for (int w2 = 0; w2 < NW; w2++) {
+            tg += rp[w2];
+            tl += rp[16 + w2];
+            tk += rp[32 + w2];
+          }
         }
-        __syncthreads();  // red_s is rewritten by the next document
+        if constexpr (CL > 1)
+          cg::this_cluster().sync();  // red_s is rewritten by the next document
+        else
+          __syncthreads();
         if (owner) ss_acc += digamma_literal(g_new) - digamma_literal(tg);
-        if (tid == 0) {
+        if (tid == 0 && crank == 0) {
           double ll = lik_alpha + (tl - lgamma(tg)) + tk;
           long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
           atomicAdd(a.ll_counter, (unsigned long long)c);
@@ -554,6 +628,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
   }
   // DocumentMapper.close (DocumentMapper.java:354-361)
   if (owner && ss_acc != 0.0) atomicAdd(a.alpha_ss + col, ss_acc);
+  if constexpr (CL > 1) cg::this_cluster().sync();  // nobody may exit while its shared memory is read
   if (rt > 0) {
     tmem_fence_before_sync();
     __syncthreads();
@@ -562,7 +637,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
 }
 
 struct Estep2Variant {
-  int NW, CPW, RREG, WPS;
+  int NW, CPW, RREG, WPS, CL;
   cudaError_t (*launch)(const EstepArgs &, int grid, int cap_rows, size_t smem, cudaStream_t);
   size_t (*smem_bytes)(int rsm, int cap_rows);
   cudaError_t (*prepare)(size_t smem);
@@ -572,26 +647,56 @@ template <int NW, int CPW>
 static size_t variant2_smem(int rsm, int cap_rows) {
   return estep2_smem_bytes<NW, CPW>(rsm, cap_rows);
 }
-template <int NW, int CPW, int RREG, int WPS>
+template <int NW, int CPW, int RREG, int WPS, int CL>
 static cudaError_t variant2_prepare(size_t smem) {
-  return cudaFuncSetAttribute(estep2_kernel<NW, CPW, RREG, WPS>,
+  return cudaFuncSetAttribute(estep2_kernel<NW, CPW, RREG, WPS, CL>,
                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <int NW, int CPW, int RREG, int WPS>
+template <int NW, int CPW, int RREG, int WPS, int CL>
 static cudaError_t variant2_launch(const EstepArgs &args, int grid, int cap_rows, size_t smem,
                                    cudaStream_t st) {
   EstepArgs a = args;
   a.cap_rows = cap_rows;
-  estep2_kernel<NW, CPW, RREG, WPS><<<grid, NW * 32, smem, st>>>(a);
-  return cudaGetLastError();
+  if constexpr (CL == 1) {
+    estep2_kernel<NW, CPW, RREG, WPS, CL><<<grid, NW * 32, smem, st>>>(a);
+    return cudaGetLastError();
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // documents are dealt round-robin to the clusters of the grid, so every cluster must be
+    // resident from the start: clamp the grid to what the GPU can co-schedule (cluster placement
+    // leaves some SMs unused: 132 of 148 CTAs at cluster size 4)
+    int max_clusters = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, estep2_kernel<NW, CPW, RREG, WPS, CL>, &cfg);
+    if (e != cudaSuccess) return e;
+    if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
+    if (grid / CL > max_clusters) cfg.gridDim = dim3((unsigned)(max_clusters * CL));
+    return cudaLaunchKernelEx(&cfg, estep2_kernel<NW, CPW, RREG, WPS, CL>, a);
+  }
 }
 
-#define MRLDA_VARIANT2R(NW_, CPW_, RREG_, WPS_)                                                  \
-  {                                                                                              \
-    NW_, CPW_, RREG_, WPS_, variant2_launch<NW_, CPW_, RREG_, WPS_>, variant2_smem<NW_, CPW_>,   \
-        variant2_prepare<NW_, CPW_, RREG_, WPS_>                                                 \
+#define MRLDA_VARIANT2R(NW_, CPW_, RREG_, WPS_)                                                     \
+  {                                                                                                 \
+    NW_, CPW_, RREG_, WPS_, 1, variant2_launch<NW_, CPW_, RREG_, WPS_, 1>, variant2_smem<NW_, CPW_>, \
+        variant2_prepare<NW_, CPW_, RREG_, WPS_, 1>                                                 \
   }
 #define MRLDA_VARIANT2(NW_, CPW_, WPS_) MRLDA_VARIANT2R(NW_, CPW_, estep2_rreg(CPW_, WPS_), WPS_)
+// cluster variants: 8 warps x 255 registers per CTA, CL CTAs per document
+#define MRLDA_VARIANT2C(CPW_, CL_)                                                                   \
+  {                                                                                                  \
+    8, CPW_, estep2_rreg(CPW_, 8), 8, CL_, variant2_launch<8, CPW_, estep2_rreg(CPW_, 8), 8, CL_>,   \
+        variant2_smem<8, CPW_>, variant2_prepare<8, CPW_, estep2_rreg(CPW_, 8), 8, CL_>              \
+  }
 
 extern const Estep2Variant g_estep2_variants_W1[];
 extern const int g_estep2_variants_W1_n;
@@ -603,5 +708,9 @@ extern const Estep2Variant g_estep2_variants_W8[];
 extern const int g_estep2_variants_W8_n;
 extern const Estep2Variant g_estep2_variants_W16[];
 extern const int g_estep2_variants_W16_n;
+extern const Estep2Variant g_estep2_variants_C2[];
+extern const int g_estep2_variants_C2_n;
+extern const Estep2Variant g_estep2_variants_C4[];
+extern const int g_estep2_variants_C4_n;
 
 }  // namespace mrlda

@@ -497,33 +497,36 @@ static const EstepVariant *select_variant(int K) {
 
 static const Estep2Variant *select_variant2(int K) {
   const Estep2Variant *tabs[] = {g_estep2_variants_W1, g_estep2_variants_W2, g_estep2_variants_W4,
-                                 g_estep2_variants_W8, g_estep2_variants_W16};
+                                 g_estep2_variants_W8, g_estep2_variants_W16, g_estep2_variants_C2,
+                                 g_estep2_variants_C4};
   const int ns[] = {g_estep2_variants_W1_n, g_estep2_variants_W2_n, g_estep2_variants_W4_n,
-                    g_estep2_variants_W8_n, g_estep2_variants_W16_n};
+                    g_estep2_variants_W8_n, g_estep2_variants_W16_n, g_estep2_variants_C2_n,
+                    g_estep2_variants_C4_n};
   const char *force = getenv("MRLDA_ESTEP2_VARIANT");  // "NW,CPW[,RREG]" — profiling aid
   int fw = 0, fc = 0, fr = 0;
   if (force && sscanf(force, "%d,%d,%d", &fw, &fc, &fr) < 2) fw = fc = fr = 0;
   const char *ew = getenv("MRLDA_ESTEP2_WPS");  // warps per SM class: 8 or 16
   const int wps = ew ? atoi(ew) : MRLDA_DEFAULT_WPS;
   const int max_cpw = wps == 16 ? 16 : 26;
-  // fewest warps per CTA whose column slice stays <= max_cpw doubles, then the narrowest slice
+  // fewest warps per CTA whose column slice stays <= max_cpw doubles, then the narrowest slice;
+  // beyond 8 warps x 32 columns the topic split continues across a cluster of 2 or 4 CTAs
   const Estep2Variant *best = nullptr;
-  for (int t = 0; t < 5; t++) {
+  for (int t = 0; t < 7; t++) {
     for (int i = 0; i < ns[t]; i++) {
       const Estep2Variant *v = &tabs[t][i];
-      if (v->NW * v->CPW < K) continue;
+      if (v->CL * v->NW * v->CPW < K) continue;
       if (fw) {
-        if (v->NW == fw && v->CPW == fc && (fr ? v->RREG == fr : v->RREG == estep2_rreg(v->CPW, v->WPS)) &&
-            (!ew || v->WPS == wps))
+        if (v->CL == 1 && v->NW == fw && v->CPW == fc &&
+            (fr ? v->RREG == fr : v->RREG == estep2_rreg(v->CPW, v->WPS)) && (!ew || v->WPS == wps))
           return v;
         continue;
       }
-      if (v->WPS != wps || v->RREG != estep2_rreg(v->CPW, v->WPS)) continue;
+      if (v->WPS != (t >= 5 ? 8 : wps) || v->RREG != estep2_rreg(v->CPW, v->WPS)) continue;
       if (!best || v->CPW < best->CPW) best = v;
     }
     if (best) {
-      if (best->CPW <= max_cpw) return best;
-      if (t < 4) best = nullptr;  // slice too wide at this warp count: try more warps
+      if (best->CPW <= max_cpw || t >= 3) return best;
+      best = nullptr;  // slice too wide at this warp count: try more warps
     }
   }
   return best;
@@ -607,7 +610,8 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   ctx->KS = ctx->variant->L * ctx->variant->KPL;
   ctx->variant2 = select_variant2(ctx->K);
   ctx->ES = ctx->KS;
-  if (ctx->variant2) ctx->ES = std::max(ctx->ES, ctx->variant2->NW * ctx->variant2->CPW);
+  if (ctx->variant2)
+    ctx->ES = std::max(ctx->ES, ctx->variant2->CL * ctx->variant2->NW * ctx->variant2->CPW);
   auto fail = [&](int code) {
     g_global_error = ctx->err;
     mrlda_destroy(ctx);
@@ -1111,7 +1115,8 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       n_long = (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), cap2,
                                       [](int cap, int32_t nn) { return cap >= nn; }) -
                      ctx->h_nnz_sorted.begin());
-      grid2 = (int)std::min<int64_t>((int64_t)c2 * ctx->num_sms, ctx->D - n_long);
+      // a cluster variant runs CL CTAs per document; the grid is a whole number of clusters
+      grid2 = v2->CL * (int)std::min<int64_t>((int64_t)c2 * ctx->num_sms / v2->CL, ctx->D - n_long);
       // never let more than c2 CTAs share an SM: they would over-subscribe its 512 TMEM columns
       // and the extra CTA's tcgen05.alloc would wait forever
       const size_t min_dyn = (size_t)233472 / (c2 + 1) - 1024 + 16;
@@ -1139,7 +1144,20 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
     a.doc_begin = n_long;
     a.doc_end = (int)ctx->D;
     a.work_counter = ctx->d_work + 2;
-    CK(ctx->variant2->launch(a, grid2, cap2, smem2, st));
+    cudaError_t e2 = ctx->variant2->launch(a, grid2, cap2, smem2, st);
+    if (e2 == cudaErrorLaunchOutOfResources && ctx->variant2->CL > 1) {
+      // no cluster of this size can be scheduled on this device: the general kernel (still CUDA,
+      // never the host) takes these documents as well
+      cudaGetLastError();
+      plan_estep(ctx, &c, &t, &cap, &smem);
+      CK(ctx->variant->prepare(smem));
+      a.cap_rows = cap;
+      a.work_counter = ctx->d_work + 3;
+      int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, ctx->D - n_long);
+      CK(ctx->variant->launch(a, grid, t, cap, st));
+    } else {
+      CK(e2);
+    }
     ctx->launches++;
   }
   CK(cudaEventRecord(ctx->ev[2], st));
