@@ -55,8 +55,7 @@ def generate(D, V, K, mean_len, seed=0, heavy_tail=False, device="cpu", chunk_to
     f64 = torch.float64
 
     def gamma_rand(shape, conc):
-        # Marsaglia-free: Gamma(a) for a < 1 via Gamma(a+1) * U^(1/a); Gamma(a+1) ~ sum trick is
-        # overkill here, torch's _standard_gamma honours the generator on both backends.
+        # torch's _standard_gamma honours the generator on both the CPU and the CUDA backend
         a = torch.full(shape, conc, dtype=f64, device=dev)
         return torch._standard_gamma(a, generator=g).clamp_min_(1e-300)
 

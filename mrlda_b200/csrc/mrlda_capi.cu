@@ -1080,10 +1080,6 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.slow_rows = ctx->d_work + 1;
   a.phase_cycles = ctx->d_phase;
   a.tmem_slots = 0;
-  {
-    const char *rs = getenv("MRLDA_ESTEP2_RS");  // profiling aid: 1 = shared-memory transpose
-    a.rs_smem = rs ? atoi(rs) : 0;
-  }
   a.K = K;
   a.sweeps = ctx->cfg.sweep_cap - 1;
   a.use_stored_gamma = (ctx->gamma_valid && !ctx->cfg.random_start) ? 1 : 0;
