@@ -1047,6 +1047,12 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
     set_err(ctx, "mrlda_e_step: %s not set", !ctx->d_row_ptr ? "corpus" : !ctx->alpha_set ? "alpha" : "beta");
     return MRLDA_ESTATE;
   }
+  if (ctx->D <= 0) {
+    // a job without input records leaves no alpha statistics file and the reference's driver fails
+    // on importAlpha (VariationalInference.java:288-289); fail here instead of producing NaNs
+    set_err(ctx, "mrlda_e_step: the corpus of this rank has no documents");
+    return MRLDA_ESTATE;
+  }
   CK(cudaSetDevice(ctx->cfg.device));
   cudaStream_t st = ctx->stream;
   const int K = ctx->K;
