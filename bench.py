@@ -127,6 +127,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's documents")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp32", action="store_true", help="optional fp32 mode (1e-4 tolerance); not the default")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -205,7 +206,7 @@ def main():
     gamma_out_t = torch.empty((mine.n_docs, K), dtype=torch.float64).pin_memory()
     gamma_out = gamma_out_t.numpy()
 
-    ctx = capi.Context(K, V, device=local_rank, rank=rank, world_size=world)
+    ctx = capi.Context(K, V, device=local_rank, rank=rank, world_size=world, fp32_mode=int(args.fp32))
     if world > 1:
         idt = torch.zeros(capi.MRLDA_NCCL_ID_BYTES, dtype=torch.uint8)
         if rank == 0:
@@ -309,7 +310,8 @@ def main():
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall_max / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 tile / f64 elsewhere (optional mode)" if args.fp32 else "f64",
             "data": "synthetic",
             "config": dict(wl, docs=full.n_docs, nnz=full.nnz, tokens=total_tokens,
                            parallelism=f"documents sharded by nnz over {world} GPU(s)",

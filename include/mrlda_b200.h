@@ -57,6 +57,9 @@ typedef struct mrlda_config {
   int32_t rank;            /* document-shard rank (0 when single GPU)                          */
   int32_t world_size;      /* number of document shards / GPUs (1 when single GPU)             */
   int32_t update_alpha;    /* 1 = run the alpha update inside mrlda_iterate (default)          */
+  int32_t fp32_mode;       /* 0 = fp64 (default, 1e-9 parity); 1 = optional fp32 E-step tile:
+                              single-precision E / dot products / S, everything else fp64;
+                              stated tolerance 1e-4 on ELBO and logbeta                         */
   double eta;              /* Settings.DEFAULT_LOG_ETA = log(1e-12) -> eta = 1e-12              */
   uint64_t seed;           /* seed for mrlda_init_beta_random (the reference uses Math.random)  */
 } mrlda_config;

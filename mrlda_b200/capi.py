@@ -29,7 +29,8 @@ class MrldaConfig(C.Structure):
         ("n_topics", C.c_int32), ("n_terms", C.c_int32), ("sweep_cap", C.c_int32),
         ("learning", C.c_int32), ("random_start", C.c_int32), ("symmetric_alpha", C.c_int32),
         ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
-        ("update_alpha", C.c_int32), ("eta", C.c_double), ("seed", C.c_uint64),
+        ("update_alpha", C.c_int32), ("fp32_mode", C.c_int32), ("eta", C.c_double),
+        ("seed", C.c_uint64),
     ]
 
 

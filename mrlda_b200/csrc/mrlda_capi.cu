@@ -23,7 +23,7 @@
 #include <vector>
 
 #include "../../include/mrlda_b200.h"
-#include "estep2_kernel.cuh"
+#include "estep2f_kernel.cuh"
 
 using namespace mrlda;
 
@@ -415,6 +415,7 @@ struct mrlda_ctx {
   int K = 0, V = 0, KS = 0;
   const EstepVariant *variant = nullptr;    // general kernel (any document length)
   const Estep2Variant *variant2 = nullptr;  // register-stationary kernel (documents that fit one SM)
+  const Estep2fVariant *variant2f = nullptr;  // fp32-mode counterpart of variant2 (same NW, CPW)
   int ES = 0;                               // row stride of E in doubles
   std::vector<int32_t> h_nnz_sorted;        // nnz per document in doc_order (descending)
   int num_sms = 0;
@@ -532,9 +533,21 @@ static const Estep2Variant *select_variant2(int K) {
   return best;
 }
 
+static const Estep2fVariant *select_variant2f(const Estep2Variant *v2) {
+  if (!v2 || v2->CL != 1 || v2->WPS != 8) return nullptr;
+  const Estep2fVariant *tabs[] = {g_estep2f_variants_W1, g_estep2f_variants_W2, g_estep2f_variants_W4,
+                                  g_estep2f_variants_W8};
+  const int ns[] = {g_estep2f_variants_W1_n, g_estep2f_variants_W2_n, g_estep2f_variants_W4_n,
+                    g_estep2f_variants_W8_n};
+  for (int t = 0; t < 4; t++)
+    for (int i = 0; i < ns[t]; i++)
+      if (tabs[t][i].NW == v2->NW && tabs[t][i].CPW == v2->CPW) return &tabs[t][i];
+  return nullptr;
+}
+
 extern "C" {
 
-const char *mrlda_version(void) { return "mrlda_b200 0.1 (sm_100a, fp64)"; }
+const char *mrlda_version(void) { return "mrlda_b200 0.1 (sm_100a, fp64 + optional fp32 E-step)"; }
 
 void mrlda_default_config(mrlda_config *cfg) {
   memset(cfg, 0, sizeof *cfg);
@@ -609,6 +622,7 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   }
   ctx->KS = ctx->variant->L * ctx->variant->KPL;
   ctx->variant2 = select_variant2(ctx->K);
+  ctx->variant2f = cfg->fp32_mode ? select_variant2f(ctx->variant2) : nullptr;
   ctx->ES = ctx->KS;
   if (ctx->variant2)
     ctx->ES = std::max(ctx->ES, ctx->variant2->CL * ctx->variant2->NW * ctx->variant2->CPW);
@@ -1099,7 +1113,26 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   size_t smem2 = 0;
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");  // "1": general kernel only (test / profiling aid)
   const bool use2 = ctx->variant2 && !(fk && atoi(fk) == 1);
-  if (use2 && ctx->D > 0) {
+  const bool use2f = use2 && ctx->variant2f != nullptr;
+  if (use2f && ctx->D > 0) {
+    // optional fp32 mode: registers then Tensor Memory only; longer documents take the fp64 general kernel
+    const Estep2fVariant *vf = ctx->variant2f;
+    const int c2 = 8 / vf->NW;
+    const size_t per = std::min(((size_t)233472 - (size_t)c2 * 1024) / c2, ctx->smem_optin) & ~(size_t)15;
+    const int need_slots = (ctx->max_rows + 31) / 32;
+    int rt = std::max(0, std::min(estep2f_tmem_slots(vf->NW, vf->CPW), need_slots - vf->RREG));
+    cap2 = 32 * (vf->RREG + rt);
+    a.tmem_slots = rt;
+    if (vf->smem_bytes(cap2) <= per) {
+      n_long = (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), cap2,
+                                      [](int cap, int32_t nn) { return cap >= nn; }) -
+                     ctx->h_nnz_sorted.begin());
+      grid2 = (int)std::min<int64_t>((int64_t)c2 * ctx->num_sms, ctx->D - n_long);
+      const size_t min_dyn = (size_t)233472 / (c2 + 1) - 1024 + 16;
+      smem2 = std::max(vf->smem_bytes(cap2), std::min(min_dyn, per));
+      if (grid2 > 0) CK(vf->prepare(smem2));
+    }
+  } else if (use2 && ctx->D > 0) {
     const Estep2Variant *v2 = ctx->variant2;
     const int c2 = v2->WPS / v2->NW;
     const size_t per = std::min(((size_t)233472 - (size_t)c2 * 1024) / c2, ctx->smem_optin) & ~(size_t)15;
@@ -1146,7 +1179,8 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
     a.doc_begin = n_long;
     a.doc_end = (int)ctx->D;
     a.work_counter = ctx->d_work + 2;
-    cudaError_t e2 = ctx->variant2->launch(a, grid2, cap2, smem2, st);
+    cudaError_t e2 = use2f ? ctx->variant2f->launch(a, grid2, cap2, smem2, st)
+                           : ctx->variant2->launch(a, grid2, cap2, smem2, st);
     if (e2 == cudaErrorLaunchOutOfResources && ctx->variant2->CL > 1) {
       // no cluster of this size can be scheduled on this device: the general kernel (still CUDA,
       // never the host) takes these documents as well

@@ -284,6 +284,42 @@ def test_informed_prior_changes_eta_per_cell(capi, oracle):
     assert rel_err(dl[seen], plain["digamma_lambda"][seen]) > 1e-3  # the prior really acted
 
 
+@pytest.mark.parametrize("K", [8, 20, 100, 200])
+def test_fp32_mode(capi, oracle, K):
+    """Optional fp32 mode (single-precision tile / dot products / S, everything else fp64).
+
+    Stated tolerance: per-iteration ELBO within 1e-6 relative always; logbeta (max over
+    all cells) within 1e-4 once the topics have separated (from the third iteration of a fit), and
+    within 5e-3 in the first two iterations from the reference's random initial beta, where the
+    topics are near-identical and the split of a document's mass between them is ill-conditioned
+    (the same amplification turns 1e-16 into ~1e-12 in fp64).  Each GPU iteration is compared with
+    the oracle run on the same inputs."""
+    from mrlda_b200 import corpus
+    c = small_corpus(D=60, V=500, K=K, mean_len=80, seed=100 + K)
+    alpha = np.full(K, 1e-3)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=K)
+    with capi.Context(K, c.n_terms, fp32_mode=1) as ctx:
+        ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count)
+        ctx.set_alpha(alpha)
+        ctx.set_logbeta(lb)
+        g_alpha, g_lb, g_gamma = alpha, lb, None
+        for it in range(3):
+            r = ctx.iterate()
+            ref = oracle.iterate(K, c.n_terms, c.row_ptr, c.term_id, c.count, g_lb, g_alpha,
+                                 gamma=g_gamma)
+            seen = ref["present"].astype(bool)
+            g_lb, g_alpha, g_gamma = ctx.get_logbeta(), ctx.get_alpha(), ctx.get_gamma()
+            assert r["n_docs"] == c.n_docs and r["n_tokens"] == c.n_tokens
+            assert np.array_equal(ctx.get_beta()[2], ref["present"])
+            assert abs(r["log_likelihood"] - ref["log_likelihood"]) <= 1e-6 * abs(ref["log_likelihood"])
+            assert _lb_err(g_lb[seen], ref["logbeta"][seen]) < (5e-3 if it < 2 else 1e-4), it
+            assert rel_err(g_alpha, ref["alpha"]) < 1e-5
+    # and it really ran in single precision: not bit-identical to the fp64 mode
+    out64, _ = _run_pair(capi, oracle, c, alpha, lb)
+    out32, _ = _run_pair(capi, oracle, c, alpha, lb, fp32_mode=1)
+    assert rel_err(out32["gamma"], out64["gamma"]) > 1e-12
+
+
 def test_alpha_known_answers_on_device(capi):
     """The reference's own KATs (VariationalInferenceTest.java:27-62) through the device kernels."""
     with capi.Context(3, 10) as ctx:

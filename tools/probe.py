@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--max-rows", type=int, default=1 << 30)
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--sweep-cap", type=int, default=100)
+    ap.add_argument("--fp32", action="store_true", help="optional fp32 mode")
     args = ap.parse_args()
     D0, V, K, mean_len, heavy = corpus.SHAPES[args.workload]
     c = corpus.generate(args.docs, V, K, mean_len, seed=4, heavy_tail=heavy, device="cuda")
@@ -34,7 +35,7 @@ def main():
         idx = np.concatenate([np.arange(c.row_ptr[d], c.row_ptr[d + 1]) for d in keep])
         c = corpus.Corpus(rp, c.term_id[idx], c.count[idx], V, K)
     n = np.diff(c.row_ptr)
-    with capi.Context(K, V, sweep_cap=args.sweep_cap) as ctx:
+    with capi.Context(K, V, sweep_cap=args.sweep_cap, fp32_mode=int(args.fp32)) as ctx:
         ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count)
         ctx.set_alpha(np.full(K, 1e-3))
         ctx.set_logbeta(corpus.init_logbeta(V, K, seed=7))
