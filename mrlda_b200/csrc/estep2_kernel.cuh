@@ -42,6 +42,17 @@
 
 namespace mrlda {
 
+template <int NW, int CPW, int RREG, int WPS>
+struct Estep2Shape {
+  static constexpr int THREADS = NW * 32;
+  static constexpr int CTAS_PER_SM = WPS / NW;
+  static constexpr int KS = NW * CPW;
+  static constexpr int HALF = CPW / 2;
+  static_assert(CPW % 2 == 0 && CPW <= 32, "CPW must be even and at most 32");
+  static_assert(NW == 1 || NW == 2 || NW == 4 || NW == 8 || NW == 16, "NW in {1,2,4,8,16}");
+  static_assert((WPS == 8 || WPS == 16) && NW <= WPS, "WPS in {8,16}");
+};
+
 // TMEM slot stride in 32-bit columns: one tcgen05.ld.32x32b.xS fetches a slot (2*CPW words used)
 __host__ __device__ constexpr int estep2_tmem_stride(int cpw) {
   return 2 * cpw > 32 ? 64 : (2 * cpw > 16 ? 32 : (2 * cpw > 8 ? 16 : 8));
@@ -466,11 +477,29 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         estep2_sweep<NW, CPW, RREG, CL, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank);
       MRLDA_TICK(6);
-      // (4) S_c to the owner lane: reduce-scatter across the lanes in registers (27 exchanges for
-      // 26 columns).  A transpose through shared memory was measured slower (1100 vs 700 cycles): it
-      // costs more wavefronts on the same LSU port than the 54 shuffles do.
+      // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
+      // document leaves it free, else reduce-scatter in registers
       double S_c;
-      {
+      if (a.rs_smem && rsm > 0 && nslots < RREG + rt + rsm) {
+        double *scr = es + ((size_t)(rsm - 1) * NW + warp) * 32 * CPW;
+#pragma unroll
+        for (int c = 0; c < CPW; c++) scr[c * 32 + lane] = s[c];
+        __syncwarp();
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        if (lane < CPW) {
+          const double *colp = scr + lane * 32;
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            double2 v = *reinterpret_cast<const double2 *>(colp + 2 * ((i + lane) & 15));
+            double2 u = *reinterpret_cast<const double2 *>(colp + 2 * ((i + 1 + lane) & 15));
+            a0 += v.x;
+            a1 += v.y;
+            a2 += u.x;
+            a3 += u.y;
+          }
+        }
+        S_c = (a0 + a1) + (a2 + a3);
+      } else {
         int base = 0, cnt = CPW;
         reduce_scatter<CPW, 16, 1, CPW>(s, lane, base, cnt);
         S_c = __shfl_sync(0xffffffffu, s[0], rs_src);

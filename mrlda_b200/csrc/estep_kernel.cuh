@@ -63,6 +63,7 @@ struct EstepArgs {
   int learning;
   int cap_rows;  // tile capacity in rows (multiple of RPB)
   int tmem_slots;  // register-stationary kernel: slots per thread kept in Tensor Memory
+  int rs_smem;   // register-stationary kernel: transpose S through shared memory (1) or shuffles (0)
 };
 
 #define MRLDA_NORM_TINY 1e-200
@@ -273,7 +274,7 @@ estep_kernel(const EstepArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, T = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, NW = T >> 5;
-  const int j = lane % L;
+  const int g = lane / L, j = lane % L;
   const int K = a.K;
   const int cap = a.cap_rows;
 
