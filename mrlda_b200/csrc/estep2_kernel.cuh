@@ -60,8 +60,62 @@ __host__ __device__ constexpr int estep2_tmem_stride(int cpw) {
 // TMEM columns a CTA allocates (all co-resident CTAs together own the 512 columns of the SM) and
 // the slots each thread gets out of them (warps w and w+4 share a lane quarter and split columns)
 __host__ __device__ constexpr int estep2_tmem_cols(int nw, int wps) { return 512 / (wps / nw); }
+// Columns of a slot that live in TMEM.  tcgen05.ld accepts any column offset (measured:
+// tools/microbench/tmem_align.cu), so slots are packed without padding; when dropping up to two
+// columns of the slice makes one more slot fit into the thread's TMEM columns, those "tail" columns
+// go to a small thread-private shared-memory array instead (K=200: 24 of 26 columns = 48 words per
+// slot, 5 slots in 256 words instead of 4).
+__host__ __device__ constexpr int estep2_tmem_words_per_thread(int nw, int wps) {
+  return estep2_tmem_cols(nw, wps) / (nw > 4 ? nw / 4 : 1);
+}
+__host__ __device__ constexpr int estep2_tmem_slot_cols(int nw, int cpw, int wps) {
+  const int avail = estep2_tmem_words_per_thread(nw, wps);
+  int best = cpw;
+  for (int tc = cpw; tc >= cpw - 2 && tc >= 4; tc -= 2)  // multiples of 4 words only below
+    if ((2 * tc) % 8 == 0 && avail / (2 * tc) > avail / (2 * best)) best = tc;
+  return best;
+}
 __host__ __device__ constexpr int estep2_tmem_slots(int nw, int cpw, int wps) {
-  return estep2_tmem_cols(nw, wps) / (nw > 4 ? nw / 4 : 1) / estep2_tmem_stride(cpw);
+  return estep2_tmem_words_per_thread(nw, wps) / (2 * estep2_tmem_slot_cols(nw, cpw, wps));
+}
+// load / store W consecutive words of my TMEM lane as power-of-two vectors
+template <int W, int OFF = 0>
+__device__ __forceinline__ void tmem_ld_words(uint32_t addr, uint32_t *w) {
+  if constexpr (W >= 64) {
+    TmemVec<64>::ld(addr + OFF, *reinterpret_cast<uint32_t(*)[64]>(w + OFF));
+    tmem_ld_words<W - 64, OFF + 64>(addr, w);
+  } else if constexpr (W >= 32) {
+    TmemVec<32>::ld(addr + OFF, *reinterpret_cast<uint32_t(*)[32]>(w + OFF));
+    tmem_ld_words<W - 32, OFF + 32>(addr, w);
+  } else if constexpr (W >= 16) {
+    TmemVec<16>::ld(addr + OFF, *reinterpret_cast<uint32_t(*)[16]>(w + OFF));
+    tmem_ld_words<W - 16, OFF + 16>(addr, w);
+  } else if constexpr (W >= 8) {
+    TmemVec<8>::ld(addr + OFF, *reinterpret_cast<uint32_t(*)[8]>(w + OFF));
+    tmem_ld_words<W - 8, OFF + 8>(addr, w);
+  } else if constexpr (W >= 4) {
+    TmemVec<4>::ld(addr + OFF, *reinterpret_cast<uint32_t(*)[4]>(w + OFF));
+    tmem_ld_words<W - 4, OFF + 4>(addr, w);
+  }
+}
+template <int W, int OFF = 0>
+__device__ __forceinline__ void tmem_st_words(uint32_t addr, const uint32_t *w) {
+  if constexpr (W >= 64) {
+    TmemVec<64>::st(addr + OFF, *reinterpret_cast<const uint32_t(*)[64]>(w + OFF));
+    tmem_st_words<W - 64, OFF + 64>(addr, w);
+  } else if constexpr (W >= 32) {
+    TmemVec<32>::st(addr + OFF, *reinterpret_cast<const uint32_t(*)[32]>(w + OFF));
+    tmem_st_words<W - 32, OFF + 32>(addr, w);
+  } else if constexpr (W >= 16) {
+    TmemVec<16>::st(addr + OFF, *reinterpret_cast<const uint32_t(*)[16]>(w + OFF));
+    tmem_st_words<W - 16, OFF + 16>(addr, w);
+  } else if constexpr (W >= 8) {
+    TmemVec<8>::st(addr + OFF, *reinterpret_cast<const uint32_t(*)[8]>(w + OFF));
+    tmem_st_words<W - 8, OFF + 8>(addr, w);
+  } else if constexpr (W >= 4) {
+    TmemVec<4>::st(addr + OFF, *reinterpret_cast<const uint32_t(*)[4]>(w + OFF));
+    tmem_st_words<W - 4, OFF + 4>(addr, w);
+  }
 }
 
 // register-resident slots: what fits in 255 registers next to the working set (theta or S: 2*CPW
@@ -75,23 +129,27 @@ __host__ __device__ constexpr int estep2_rreg(int cpw, int wps = 8) {
 template <int NW, int CPW>
 __host__ __device__ constexpr size_t estep2_smem_bytes(int rsm, int cap_rows) {
   return sizeof(double) * ((size_t)rsm * NW * 32 * CPW   // E slots
+                           // tail columns of the TMEM slots (all variants here are WPS = 8)
+                           + (size_t)estep2_tmem_slots(NW, CPW, 8) * NW * 32 *
+                                 (CPW - estep2_tmem_slot_cols(NW, CPW, 8))
                            + 2 * (size_t)NW * cap_rows   // partial dots, two buffers
                            + 2 * (size_t)cap_rows        // counts, r
                            + 3 * (size_t)NW * CPW        // theta, gamma, gextra
                            + 96);                        // reductions + doc meta
 }
 
-template <int NW, int CPW, int RREG, int CL, bool LAST>
+template <int NW, int CPW, int RREG, int WPS, int CL, bool LAST>
 __device__ __forceinline__ void estep2_sweep(
     const EstepArgs &a, double (&e)[RREG][CPW], const double *es, double *part, const double *cnt_s,
     double *r_s, int *flag_s, const double *theta_w, double (&s)[CPW], double &lik,
     unsigned &badbits, const int64_t b, const int n, const int nslots, const int cap_rows,
     const int warp, const int lane, long long *tm, const uint32_t tbase, const int rt,
-    const int crank) {
+    const int crank, const double *tail_s) {
   (void)tm;
   namespace cg = cooperative_groups;
   const int gwarp = crank * NW + warp;  // position of my warp's column slice among all CL*NW slices
-  constexpr int HALF = CPW / 2, TS = estep2_tmem_stride(CPW);
+  constexpr int HALF = CPW / 2;
+  constexpr int TC = estep2_tmem_slot_cols(NW, CPW, WPS), TW = 2 * TC, T2 = CPW - TC;
   // slot q lives in registers (q < RREG), in TMEM (q < RREG + rt) or in shared memory
   const int nt_end = nslots < RREG + rt ? nslots : RREG + rt;
   const int K = a.K;
@@ -124,24 +182,30 @@ __device__ __forceinline__ void estep2_sweep(
       th[2 * i + 1] = tv.y;
     }
     // TMEM slots (a second load buffer for software pipelining does not fit the register file)
-    auto dot_words = [&](const uint32_t (&w32)[TS]) -> double {
+    for (int q = RREG; q < nt_end; q++) {
+      uint32_t w32[TW];
+      tmem_ld_words<TW>(tbase + (uint32_t)(q - RREG) * TW, w32);
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      if constexpr (T2 > 0) {  // tail columns of the slot: thread-private shared memory
+        const double *tp = tail_s + ((size_t)((q - RREG) * NW + warp) * 32 + lane) * T2;
 #pragma unroll
-      for (int i = 0; i < HALF; i += 2) {
-        a0 = fma(th[2 * i], __hiloint2double((int)w32[4 * i + 1], (int)w32[4 * i]), a0);
-        a1 = fma(th[2 * i + 1], __hiloint2double((int)w32[4 * i + 3], (int)w32[4 * i + 2]), a1);
-        if (i + 1 < HALF) {
-          a2 = fma(th[2 * i + 2], __hiloint2double((int)w32[4 * i + 5], (int)w32[4 * i + 4]), a2);
-          a3 = fma(th[2 * i + 3], __hiloint2double((int)w32[4 * i + 7], (int)w32[4 * i + 6]), a3);
+        for (int c = 0; c < T2; c += 2) {
+          const double2 v = *reinterpret_cast<const double2 *>(tp + c);
+          a2 = fma(th[TC + c], v.x, a2);
+          a3 = fma(th[TC + c + 1], v.y, a3);
         }
       }
-      return (a0 + a1) + (a2 + a3);
-    };
-    for (int q = RREG; q < nt_end; q++) {
-      uint32_t w32[TS];
-      TmemVec<TS>::ld(tbase + (uint32_t)(q - RREG) * TS, w32);
       tmem_wait_ld();
-      pw[32 * q] = dot_words(w32);
+#pragma unroll
+      for (int c = 0; c < TC; c += 4) {
+        a0 = fma(th[c], __hiloint2double((int)w32[2 * c + 1], (int)w32[2 * c]), a0);
+        a1 = fma(th[c + 1], __hiloint2double((int)w32[2 * c + 3], (int)w32[2 * c + 2]), a1);
+        if (c + 2 < TC) {
+          a2 = fma(th[c + 2], __hiloint2double((int)w32[2 * c + 5], (int)w32[2 * c + 4]), a2);
+          a3 = fma(th[c + 3], __hiloint2double((int)w32[2 * c + 7], (int)w32[2 * c + 6]), a3);
+        }
+      }
+      pw[32 * q] = (a0 + a1) + (a2 + a3);
     }
     for (int q = RREG + rt; q < nslots; q++) {  // shared-memory slots
       const double2 *src = reinterpret_cast<const double2 *>(es) +
@@ -253,31 +317,30 @@ __device__ __forceinline__ void estep2_sweep(
     }
   }
   // TMEM slots
-  auto s_words = [&](int q, const uint32_t (&w32)[TS]) {
+  for (int q = RREG; q < nt_end; q++) {
+    uint32_t w32[TW];
+    tmem_ld_words<TW>(tbase + (uint32_t)(q - RREG) * TW, w32);
     double r = r_s[32 * q + lane];
     if (r < 0.0) {
       badbits |= 1u << q;
       r = 0.0;
     }
-    if (LAST) {
-      double tmp[CPW];
+    double tmp[CPW];
+    if constexpr (T2 > 0) {
+      const double *tp = tail_s + ((size_t)((q - RREG) * NW + warp) * 32 + lane) * T2;
 #pragma unroll
-      for (int c = 0; c < CPW; c++) {
-        tmp[c] = __hiloint2double((int)w32[2 * c + 1], (int)w32[2 * c]);
-        s[c] = fma(r, tmp[c], s[c]);
+      for (int c = 0; c < T2; c += 2) {
+        const double2 v = *reinterpret_cast<const double2 *>(tp + c);
+        tmp[TC + c] = v.x;
+        tmp[TC + c + 1] = v.y;
       }
-      scatter(q, r, tmp);
-    } else {
-#pragma unroll
-      for (int c = 0; c < CPW; c++)
-        s[c] = fma(r, __hiloint2double((int)w32[2 * c + 1], (int)w32[2 * c]), s[c]);
     }
-  };
-  for (int q = RREG; q < nt_end; q++) {
-    uint32_t w32[TS];
-    TmemVec<TS>::ld(tbase + (uint32_t)(q - RREG) * TS, w32);
     tmem_wait_ld();
-    s_words(q, w32);
+#pragma unroll
+    for (int c = 0; c < TC; c++) tmp[c] = __hiloint2double((int)w32[2 * c + 1], (int)w32[2 * c]);
+#pragma unroll
+    for (int c = 0; c < CPW; c++) s[c] = fma(r, tmp[c], s[c]);
+    if (LAST) scatter(q, r, tmp);
   }
   for (int q = RREG + rt; q < nslots; q++) {  // shared-memory slots
     double r = r_s[32 * q + lane];
@@ -310,13 +373,14 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int K = a.K;
-  constexpr int TS = estep2_tmem_stride(CPW);
+  constexpr int TC = estep2_tmem_slot_cols(NW, CPW, WPS), TW = 2 * TC, T2 = CPW - TC;
   const int rt = a.tmem_slots;              // slots per thread in TMEM (0: TMEM not used)
   const int cap_rows = a.cap_rows;          // 32 * (RREG + rt + rsm)
   const int rsm = cap_rows / 32 - RREG - rt;
 
   double *es = smem;                                        // rsm x NW x HALF x 32 double2
-  double *part_s = es + (size_t)rsm * NW * 32 * CPW;        // 2 x NW x cap_rows
+  double *tail_s = es + (size_t)rsm * NW * 32 * CPW;        // TMEM slots' tail columns
+  double *part_s = tail_s + (size_t)estep2_tmem_slots(NW, CPW, 8) * NW * 32 * T2;  // 2 x NW x cap_rows
   double *cnt_s = part_s + 2 * (size_t)NW * cap_rows;       // cap_rows
   double *r_s = cnt_s + cap_rows;                           // cap_rows
   double *theta_s = r_s + cap_rows;                         // KS
@@ -332,7 +396,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
     tmem_fence_before_sync();
     __syncthreads();
     tmem_fence_after_sync();
-    const uint32_t cols_per_thread = estep2_tmem_cols(NW, WPS) / (NW > 4 ? NW / 4 : 1);
+    const uint32_t cols_per_thread = estep2_tmem_words_per_thread(NW, WPS);
     tbase = (uint32_t)meta_s[2] + (((uint32_t)(warp & 3) * 32u) << 16) +
             (uint32_t)(warp >> 2) * cols_per_thread;
   }
@@ -408,24 +472,33 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       }
     }
     const int nt_end = nslots < RREG + rt ? nslots : RREG + rt;
-    for (int q = RREG; q < nt_end; q++) {  // TMEM slots
+    for (int q = RREG; q < nt_end; q++) {  // TMEM slots (+ their tail columns in shared memory)
       const int row = 32 * q + lane;
-      uint32_t w32[TS];
+      uint32_t w32[TW];
 #pragma unroll
-      for (int i = 0; i < TS; i++) w32[i] = 0u;
+      for (int i = 0; i < TW; i++) w32[i] = 0u;
+      double *tp = tail_s + ((size_t)((q - RREG) * NW + warp) * 32 + lane) * (T2 > 0 ? T2 : 1);
+      if constexpr (T2 > 0) {
+#pragma unroll
+        for (int c = 0; c < T2; c++) tp[c] = 0.0;
+      }
       if (row < n) {
         const double2 *src = reinterpret_cast<const double2 *>(
             a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW);
 #pragma unroll
         for (int i = 0; i < HALF; i++) {
           const double2 v = __ldg(src + i);
-          w32[4 * i] = (uint32_t)__double2loint(v.x);
-          w32[4 * i + 1] = (uint32_t)__double2hiint(v.x);
-          w32[4 * i + 2] = (uint32_t)__double2loint(v.y);
-          w32[4 * i + 3] = (uint32_t)__double2hiint(v.y);
+          if (2 * i < TC) {
+            w32[4 * i] = (uint32_t)__double2loint(v.x);
+            w32[4 * i + 1] = (uint32_t)__double2hiint(v.x);
+            w32[4 * i + 2] = (uint32_t)__double2loint(v.y);
+            w32[4 * i + 3] = (uint32_t)__double2hiint(v.y);
+          } else if constexpr (T2 > 0) {
+            *reinterpret_cast<double2 *>(tp + (2 * i - TC)) = v;
+          }
         }
       }
-      TmemVec<TS>::st(tbase + (uint32_t)(q - RREG) * TS, w32);
+      tmem_st_words<TW>(tbase + (uint32_t)(q - RREG) * TW, w32);
     }
     if (nt_end > RREG) tmem_wait_st();
     for (int q = RREG + rt; q < nslots; q++) {  // shared-memory slots
@@ -471,11 +544,11 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       MRLDA_TICK(1);
       double *part = part_s + (size_t)(sweep & 1) * NW * cap_rows;
       if (!last)
-        estep2_sweep<NW, CPW, RREG, CL, false>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
-                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank);
+        estep2_sweep<NW, CPW, RREG, WPS, CL, false>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
+                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank, tail_s);
       else
-        estep2_sweep<NW, CPW, RREG, CL, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
-                                          badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank);
+        estep2_sweep<NW, CPW, RREG, WPS, CL, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
+                                          badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank, tail_s);
       MRLDA_TICK(6);
       // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
       // document leaves it free, else reduce-scatter in registers
