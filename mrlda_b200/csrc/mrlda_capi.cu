@@ -421,6 +421,7 @@ struct mrlda_ctx {
   int num_sms = 0;
   size_t smem_optin = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // general E-step kernel, concurrent with the register-stationary one
   cudaEvent_t ev[8] = {};
   std::string err;
   int64_t launches = 0;
@@ -578,6 +579,7 @@ void mrlda_destroy(mrlda_ctx *ctx) {
     if (p) cudaFree(p);
   for (auto &e : ctx->ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -650,6 +652,7 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   ctx->num_sms = prop.multiProcessorCount;
   ctx->smem_optin = prop.sharedMemPerBlockOptin;
   CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
   for (auto &ev : ctx->ev) CKC(cudaEventCreate(&ev));
   const size_t K = ctx->K, V = ctx->V, KS = ctx->ES;
   CKC(cudaMalloc(&ctx->d_alpha, K * sizeof(double)));
@@ -1173,35 +1176,53 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
     CK(ctx->variant->prepare(smem));
   }
   CK(cudaEventRecord(ctx->ev[1], st));
-  if (n_long > 0) {
-    a.doc_begin = 0;
-    a.doc_end = n_long;
-    a.work_counter = ctx->d_work;
-    a.cap_rows = cap;
-    int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, n_long);
-    CK(ctx->variant->launch(a, grid, t, cap, st));
-    ctx->launches++;
-  }
-  if (grid2 > 0) {
-    a.doc_begin = n_long;
-    a.doc_end = (int)ctx->D;
-    a.work_counter = ctx->d_work + 2;
-    cudaError_t e2 = use2f ? ctx->variant2f->launch(a, grid2, cap2, smem2, st)
-                           : ctx->variant2->launch(a, grid2, cap2, smem2, st);
-    if (e2 == cudaErrorLaunchOutOfResources && ctx->variant2->CL > 1) {
-      // no cluster of this size can be scheduled on this device: the general kernel (still CUDA,
-      // never the host) takes these documents as well
-      cudaGetLastError();
-      plan_estep(ctx, &c, &t, &cap, &smem);
-      CK(ctx->variant->prepare(smem));
+  // The two kernels work on disjoint documents and only meet in atomics, so they run on two
+  // streams.  A cluster launch cannot use every SM (132 of 148 at cluster size 4): it goes first and
+  // the general kernel's persistent CTAs fill the SMs it leaves free, then the rest of the GPU once
+  // it drains.  Otherwise the general kernel (the longest documents) goes first and the
+  // register-stationary CTAs take over each SM as it runs out of long documents.
+  const bool overlap = n_long > 0 && grid2 > 0 && !getenv("MRLDA_ESTEP_SERIAL");
+  const bool cluster_first = overlap && !use2f && ctx->variant2->CL > 1;
+  // the kernel that should start first stays on the main stream (nothing to wait for); the other
+  // one goes to the second stream behind the fork event
+  if (overlap) CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev[1], 0));
+  for (int pass = 0; pass < 2; pass++) {
+    const bool long_pass = (pass == 0) != cluster_first;
+    cudaStream_t sp = (pass == 1 && overlap) ? ctx->stream2 : st;
+    if (long_pass && n_long > 0) {
+      a.doc_begin = 0;
+      a.doc_end = n_long;
+      a.work_counter = ctx->d_work;
       a.cap_rows = cap;
-      a.work_counter = ctx->d_work + 3;
-      int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, ctx->D - n_long);
-      CK(ctx->variant->launch(a, grid, t, cap, st));
-    } else {
-      CK(e2);
+      int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, n_long);
+      CK(ctx->variant->launch(a, grid, t, cap, sp));
+      ctx->launches++;
     }
-    ctx->launches++;
+    if (!long_pass && grid2 > 0) {
+      a.doc_begin = n_long;
+      a.doc_end = (int)ctx->D;
+      a.work_counter = ctx->d_work + 2;
+      cudaError_t e2 = use2f ? ctx->variant2f->launch(a, grid2, cap2, smem2, sp)
+                             : ctx->variant2->launch(a, grid2, cap2, smem2, sp);
+      if (e2 == cudaErrorLaunchOutOfResources && ctx->variant2->CL > 1) {
+        // no cluster of this size can be scheduled on this device: the general kernel (still CUDA,
+        // never the host) takes these documents as well
+        cudaGetLastError();
+        plan_estep(ctx, &c, &t, &cap, &smem);
+        CK(ctx->variant->prepare(smem));
+        a.cap_rows = cap;
+        a.work_counter = ctx->d_work + 3;
+        int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, ctx->D - n_long);
+        CK(ctx->variant->launch(a, grid, t, cap, sp));
+      } else {
+        CK(e2);
+      }
+      ctx->launches++;
+    }
+  }
+  if (overlap) {
+    CK(cudaEventRecord(ctx->ev[7], ctx->stream2));
+    CK(cudaStreamWaitEvent(st, ctx->ev[7], 0));
   }
   CK(cudaEventRecord(ctx->ev[2], st));
   int rc = exchange(ctx);
