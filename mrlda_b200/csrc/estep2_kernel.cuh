@@ -36,8 +36,15 @@
 
 #ifdef MRLDA_PHASE_TIMING
 #define MRLDA_TICK(i) tm[i] = clock64()
+// tick that issues only after the value is available (a scoreboard dependency on its register)
+#define MRLDA_TICK_DEP(i, v)                                          \
+  do {                                                                \
+    asm volatile("{.reg .b64 t_; mov.b64 t_, %0;}" ::"d"(v) : "memory"); \
+    tm[i] = clock64();                                                \
+  } while (0)
 #else
 #define MRLDA_TICK(i)
+#define MRLDA_TICK_DEP(i, v)
 #endif
 
 namespace mrlda {
@@ -138,6 +145,45 @@ __host__ __device__ constexpr size_t estep2_smem_bytes(int rsm, int cap_rows) {
                            + 96);                        // reductions + doc meta
 }
 
+// Statistics scatter of the last sweep: n_w phi_wk = r_w theta_k E_wk (DocumentMapper.java:315-329).
+// One warp per row, lanes across the CTA's columns, so that both the re-read of the E row (L2) and
+// the atomics are contiguous; the tile's own layout (lanes = rows) would spread every warp-wide
+// atomic over 32 rows.  Two rows and all their loads are in flight at a time.  Rows redone in log
+// space (r < 0) are scattered by the slow path.  Not inlined: it runs once per document and must
+// not take part in the register allocation of the sweep loop.
+static __device__ __noinline__ void estep2_scatter_stats(const int32_t *term_id, const double *E,
+                                                         const int e_stride, double *stats, const int K,
+                                                         const double *r_s, const double *theta_s,
+                                                         const int n, const int col0, const int KS,
+                                                         const int warp, const int nw, const int lane) {
+  for (int row = warp; row < n; row += 2 * nw) {
+    const int row2 = row + nw;
+    const double r0 = r_s[row], r1 = row2 < n ? r_s[row2] : 0.0;
+    const bool ok0 = r0 > 0.0, ok1 = r1 > 0.0;
+    const size_t t0 = ok0 ? (size_t)(__ldg(term_id + row) - 1) : 0;
+    const size_t t1 = ok1 ? (size_t)(__ldg(term_id + row2) - 1) : 0;
+    const double *e0 = E + t0 * e_stride + col0, *e1 = E + t1 * e_stride + col0;
+    double v0[8], v1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int k = lane + 32 * i;
+      const bool in = k < KS && col0 + k < K;
+      v0[i] = ok0 && in ? __ldg(e0 + k) : 0.0;
+      v1[i] = ok1 && in ? __ldg(e1 + k) : 0.0;
+    }
+    double *s0 = stats + t0 * K + col0, *s1 = stats + t1 * K + col0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int k = lane + 32 * i;
+      if (k < KS && col0 + k < K) {
+        const double th = theta_s[k];
+        if (ok0) atomicAdd(s0 + k, r0 * th * v0[i]);
+        if (ok1) atomicAdd(s1 + k, r1 * th * v1[i]);
+      }
+    }
+  }
+}
+
 template <int NW, int CPW, int RREG, int WPS, int CL, bool LAST>
 __device__ __forceinline__ void estep2_sweep(
     const EstepArgs &a, double (&e)[RREG][CPW], const double *es, double *part, const double *cnt_s,
@@ -147,12 +193,10 @@ __device__ __forceinline__ void estep2_sweep(
     const int crank, const double *tail_s) {
   (void)tm;
   namespace cg = cooperative_groups;
-  const int gwarp = crank * NW + warp;  // position of my warp's column slice among all CL*NW slices
   constexpr int HALF = CPW / 2;
   constexpr int TC = estep2_tmem_slot_cols(NW, CPW, WPS), TW = 2 * TC, T2 = CPW - TC;
   // slot q lives in registers (q < RREG), in TMEM (q < RREG + rt) or in shared memory
   const int nt_end = nslots < RREG + rt ? nslots : RREG + rt;
-  const int K = a.K;
   // (2) partial dot products of my rows over my warp's columns.  Register slots are processed
   // unconditionally (an unused slot holds zeros) so that the chains of different slots interleave;
   // theta is read just in time (warp-wide broadcast loads) to keep registers for the tile.
@@ -287,15 +331,6 @@ __device__ __forceinline__ void estep2_sweep(
 #pragma unroll
   for (int c = 0; c < CPW; c++) s[c] = 0.0;
   badbits = 0;
-  auto scatter = [&](int q, double r, const double *erow) {
-    // statistics scatter of the last sweep: n_w phi_wk = r_w theta_k E_wk (DocumentMapper.java:315-329)
-    if (!(r > 0.0) || !a.learning) return;
-    const int term = __ldg(a.term_id + b + 32 * q + lane);
-    double *srow = a.stats + (size_t)(term - 1) * K + gwarp * CPW;
-#pragma unroll
-    for (int c = 0; c < CPW; c++)
-      if (gwarp * CPW + c < K) atomicAdd(srow + c, r * theta_w[c] * erow[c]);
-  };
   {
     double r[RREG];
 #pragma unroll
@@ -310,10 +345,6 @@ __device__ __forceinline__ void estep2_sweep(
     for (int c = 0; c < CPW; c++) {
 #pragma unroll
       for (int q = 0; q < RREG; q++) s[c] = fma(r[q], e[q][c], s[c]);
-    }
-    if (LAST) {
-#pragma unroll
-      for (int q = 0; q < RREG; q++) scatter(q, r[q], e[q]);
     }
   }
   // TMEM slots
@@ -340,7 +371,6 @@ __device__ __forceinline__ void estep2_sweep(
     for (int c = 0; c < TC; c++) tmp[c] = __hiloint2double((int)w32[2 * c + 1], (int)w32[2 * c]);
 #pragma unroll
     for (int c = 0; c < CPW; c++) s[c] = fma(r, tmp[c], s[c]);
-    if (LAST) scatter(q, r, tmp);
   }
   for (int q = RREG + rt; q < nslots; q++) {  // shared-memory slots
     double r = r_s[32 * q + lane];
@@ -350,16 +380,12 @@ __device__ __forceinline__ void estep2_sweep(
     }
     const double2 *src = reinterpret_cast<const double2 *>(es) +
                          ((size_t)((q - RREG - rt) * NW + warp) * HALF) * 32 + lane;
-    double tmp[CPW];
 #pragma unroll
     for (int i = 0; i < HALF; i++) {
       double2 v = src[(size_t)i * 32];
-      tmp[2 * i] = v.x;
-      tmp[2 * i + 1] = v.y;
       s[2 * i] = fma(r, v.x, s[2 * i]);
       s[2 * i + 1] = fma(r, v.y, s[2 * i + 1]);
     }
-    if (LAST) scatter(q, r, tmp);
   }
 }
 
@@ -446,6 +472,10 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       round++;
     }
     if (qi >= a.doc_end) break;
+#ifdef MRLDA_PHASE_TIMING
+    const long long t_doc0 = clock64();
+    long long t_doc1 = 0, t_doc2 = 0;
+#endif
     const int d = a.doc_order[qi];
     const int64_t b = a.row_ptr[d];
     const int n = (int)(a.row_ptr[d + 1] - b);
@@ -528,17 +558,24 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         gam = alpha_c + (double)((float)a.doc_tokens[d] / (float)K);
     }
     __syncthreads();
+#ifdef MRLDA_PHASE_TIMING
+    t_doc1 = clock64();
+#endif
 
     double lik = 0.0, theta_c = 0.0;
     double s[CPW];
     unsigned badbits = 0;
     for (int sweep = 0; sweep < a.sweeps; sweep++) {
       const bool last = (sweep == a.sweeps - 1);
-      long long tm[8];
+#ifdef MRLDA_PHASE_TIMING
+      if (last) t_doc2 = clock64();
+#endif
+      long long tm[10];
       (void)tm;
-      MRLDA_TICK(0);
+      MRLDA_TICK_DEP(0, gam);
       // (1) theta_c = exp(digamma(gamma_c)) in the owner lane, broadcast within the warp
       theta_c = owner ? exp_digamma(gam) : 0.0;
+      MRLDA_TICK_DEP(8, theta_c);
       if (mycol >= 0) theta_w[mycol] = theta_c;
       __syncwarp();
       MRLDA_TICK(1);
@@ -549,7 +586,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       else
         estep2_sweep<NW, CPW, RREG, WPS, CL, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank, tail_s);
-      MRLDA_TICK(6);
+      MRLDA_TICK_DEP(6, s[CPW - 1]);
       // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
       // document leaves it free, else reduce-scatter in registers
       double S_c;
@@ -577,12 +614,13 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         reduce_scatter<CPW, 16, 1, CPW>(s, lane, base, cnt);
         S_c = __shfl_sync(0xffffffffu, s[0], rs_src);
       }
-      MRLDA_TICK(7);
+      MRLDA_TICK_DEP(7, S_c);
 #ifdef MRLDA_PHASE_TIMING
       if (blockIdx.x == 0 && tid == 0 && !last) {
         for (int i = 0; i < 7; i++) a.phase_cycles[i] += tm[i + 1] - tm[i];
         a.phase_cycles[7] += 1;
         a.phase_cycles[8] += nslots;
+        a.phase_cycles[9] += tm[8] - tm[0];  // exp(digamma) alone
       }
 #endif
       // rows whose norm underflowed: exact log-space redo by warp 0 (CTA-uniform branch: every
@@ -691,6 +729,14 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         else
           __syncthreads();
         if (owner) ss_acc += digamma_literal(g_new) - digamma_literal(tg);
+#ifdef MRLDA_PHASE_TIMING
+        if (blockIdx.x == 0 && tid == 0) {
+          a.phase_cycles[10] += t_doc1 - t_doc0;        // document load
+          a.phase_cycles[11] += t_doc2 - t_doc1;        // sweeps 1..I-1
+          a.phase_cycles[12] += clock64() - t_doc2;     // last sweep + statistics scatter + epilogue
+          a.phase_cycles[13] += 1;
+        }
+#endif
         if (tid == 0 && crank == 0) {
           double ll = lik_alpha + (tl - lgamma(tg)) + tk;
           long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
@@ -698,6 +744,11 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         }
       }
     }
+    // r and theta of the last sweep are still in shared memory (nothing rewrites them before the
+    // barrier at the top of the document loop)
+    if (a.learning)
+      estep2_scatter_stats(a.term_id + b, a.E, a.e_stride, a.stats, K, r_s, theta_s, n, crank * KS, KS,
+                           warp, NW, lane);
   }
   // DocumentMapper.close (DocumentMapper.java:354-361)
   if (owner && ss_acc != 0.0) atomicAdd(a.alpha_ss + col, ss_acc);

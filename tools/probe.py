@@ -45,9 +45,10 @@ def main():
         ph = ctx.debug_phase_cycles()
     if ph[7]:
         names = ['theta', 'dots', 'B1', 'norms', 'B2', 'S', 'RS']
-        print('phase cycles per sweep (block 0, thread 0): ' + ', '.join(f'{n}={ph[i] / ph[7]:.0f}' for i, n in enumerate(names)) + f'  total={ph[:7].sum() / ph[7]:.0f}  slots/sweep={ph[8] / ph[7]:.2f}')
-    with open(os.devnull) as _:
-        pass
+        print('phase cycles per sweep (block 0, thread 0): ' + ', '.join(f'{n}={ph[i] / ph[7]:.0f}' for i, n in enumerate(names)) + f'  total={ph[:7].sum() / ph[7]:.0f}  slots/sweep={ph[8] / ph[7]:.2f}  expdigamma={ph[9] / ph[7]:.0f}')
+    if ph[13]:
+        print(f'per document (block 0): load={ph[10] / ph[13]:.0f} sweeps={ph[11] / ph[13]:.0f} '
+              f'last+scatter+epilogue={ph[12] / ph[13]:.0f} cycles over {ph[13]} documents')
     t = min(ms) * 1e-3
     flops = (args.sweep_cap - 1) * (c.nnz * 4 * K + c.n_docs * K * 60)
     print(f"docs={c.n_docs} nnz={c.nnz} rows mean={n.mean():.1f} p90={np.percentile(n, 90):.0f} "
