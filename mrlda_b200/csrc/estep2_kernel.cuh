@@ -474,7 +474,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
     if (qi >= a.doc_end) break;
 #ifdef MRLDA_PHASE_TIMING
     const long long t_doc0 = clock64();
-    long long t_doc1 = 0, t_doc2 = 0;
+    long long t_doc1 = 0, t_doc2 = 0, t_doc3 = 0;
 #endif
     const int d = a.doc_order[qi];
     const int64_t b = a.row_ptr[d];
@@ -729,19 +729,14 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         else
           __syncthreads();
         if (owner) ss_acc += digamma_literal(g_new) - digamma_literal(tg);
-#ifdef MRLDA_PHASE_TIMING
-        if (blockIdx.x == 0 && tid == 0) {
-          a.phase_cycles[10] += t_doc1 - t_doc0;        // document load
-          a.phase_cycles[11] += t_doc2 - t_doc1;        // sweeps 1..I-1
-          a.phase_cycles[12] += clock64() - t_doc2;     // last sweep + statistics scatter + epilogue
-          a.phase_cycles[13] += 1;
-        }
-#endif
         if (tid == 0 && crank == 0) {
           double ll = lik_alpha + (tl - lgamma(tg)) + tk;
           long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
           atomicAdd(a.ll_counter, (unsigned long long)c);
         }
+#ifdef MRLDA_PHASE_TIMING
+        t_doc3 = clock64();
+#endif
       }
     }
     // r and theta of the last sweep are still in shared memory (nothing rewrites them before the
@@ -749,6 +744,15 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
     if (a.learning)
       estep2_scatter_stats(a.term_id + b, a.E, a.e_stride, a.stats, K, r_s, theta_s, n, crank * KS, KS,
                            warp, NW, lane);
+#ifdef MRLDA_PHASE_TIMING
+    if (blockIdx.x == 0 && tid == 0) {
+      a.phase_cycles[10] += t_doc1 - t_doc0;     // document load
+      a.phase_cycles[11] += t_doc2 - t_doc1;     // sweeps 1..I-1
+      a.phase_cycles[12] += t_doc3 - t_doc2;     // last sweep + epilogue
+      a.phase_cycles[14] += clock64() - t_doc3;  // statistics scatter (warp 0's share)
+      a.phase_cycles[13] += 1;
+    }
+#endif
   }
   // DocumentMapper.close (DocumentMapper.java:354-361)
   if (owner && ss_acc != 0.0) atomicAdd(a.alpha_ss + col, ss_acc);

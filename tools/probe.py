@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--sweep-cap", type=int, default=100)
     ap.add_argument("--fp32", action="store_true", help="optional fp32 mode")
+    ap.add_argument("--no-learning", action="store_true", help="test mode: no statistics scatter")
     args = ap.parse_args()
     D0, V, K, mean_len, heavy = corpus.SHAPES[args.workload]
     c = corpus.generate(args.docs, V, K, mean_len, seed=4, heavy_tail=heavy, device="cuda")
@@ -35,7 +36,8 @@ def main():
         idx = np.concatenate([np.arange(c.row_ptr[d], c.row_ptr[d + 1]) for d in keep])
         c = corpus.Corpus(rp, c.term_id[idx], c.count[idx], V, K)
     n = np.diff(c.row_ptr)
-    with capi.Context(K, V, sweep_cap=args.sweep_cap, fp32_mode=int(args.fp32)) as ctx:
+    with capi.Context(K, V, sweep_cap=args.sweep_cap, fp32_mode=int(args.fp32),
+                      learning=0 if args.no_learning else 1) as ctx:
         ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count)
         ctx.set_alpha(np.full(K, 1e-3))
         ctx.set_logbeta(corpus.init_logbeta(V, K, seed=7))
@@ -48,7 +50,7 @@ def main():
         print('phase cycles per sweep (block 0, thread 0): ' + ', '.join(f'{n}={ph[i] / ph[7]:.0f}' for i, n in enumerate(names)) + f'  total={ph[:7].sum() / ph[7]:.0f}  slots/sweep={ph[8] / ph[7]:.2f}  expdigamma={ph[9] / ph[7]:.0f}')
     if ph[13]:
         print(f'per document (block 0): load={ph[10] / ph[13]:.0f} sweeps={ph[11] / ph[13]:.0f} '
-              f'last+scatter+epilogue={ph[12] / ph[13]:.0f} cycles over {ph[13]} documents')
+              f'last+epilogue={ph[12] / ph[13]:.0f} scatter={ph[14] / ph[13]:.0f} cycles over {ph[13]} documents')
     t = min(ms) * 1e-3
     flops = (args.sweep_cap - 1) * (c.nnz * 4 * K + c.n_docs * K * 60)
     print(f"docs={c.n_docs} nnz={c.nnz} rows mean={n.mean():.1f} p90={np.percentile(n, 90):.0f} "
