@@ -59,6 +59,42 @@ __device__ __forceinline__ void reduce_scatter_f(float (&v)[CPW], int lane, int 
   }
 }
 
+// fp32 form of estep2_scatter_stats (estep2_kernel.cuh): n_w phi_wk = r_w theta_k E_wk of the last
+// sweep, evaluated in float exactly as the tile would (float r, float theta, E rounded to float), one
+// warp per row with lanes across the topics so that the E re-read and the atomics are contiguous.
+static __device__ __noinline__ void estep2f_scatter_stats(const int32_t *term_id, const double *E,
+                                                          const int e_stride, double *stats, const int K,
+                                                          const float *r_s, const float *theta_s,
+                                                          const int n, const int KS, const int warp,
+                                                          const int nw, const int lane) {
+  for (int row = warp; row < n; row += 2 * nw) {
+    const int row2 = row + nw;
+    const float r0 = r_s[row], r1 = row2 < n ? r_s[row2] : 0.0f;
+    const bool ok0 = r0 > 0.0f, ok1 = r1 > 0.0f;
+    const size_t t0 = ok0 ? (size_t)(__ldg(term_id + row) - 1) : 0;
+    const size_t t1 = ok1 ? (size_t)(__ldg(term_id + row2) - 1) : 0;
+    const double *e0 = E + t0 * e_stride, *e1 = E + t1 * e_stride;
+    float v0[8], v1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int k = lane + 32 * i;
+      const bool in = k < KS && k < K;
+      v0[i] = ok0 && in ? (float)__ldg(e0 + k) : 0.0f;
+      v1[i] = ok1 && in ? (float)__ldg(e1 + k) : 0.0f;
+    }
+    double *s0 = stats + t0 * K, *s1 = stats + t1 * K;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const int k = lane + 32 * i;
+      if (k < KS && k < K) {
+        const float th = theta_s[k];
+        if (ok0) atomicAdd(s0 + k, (double)(r0 * th * v0[i]));
+        if (ok1) atomicAdd(s1 + k, (double)(r1 * th * v1[i]));
+      }
+    }
+  }
+}
+
 template <int NW, int CPW, int RREG>
 __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArgs a) {
   constexpr int HALF = CPW / 2, KS = NW * CPW, TS = estep2f_tmem_stride(CPW);
@@ -251,14 +287,6 @@ __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArg
 #pragma unroll
       for (int c = 0; c < CPW; c++) s[c] = 0.0f;
       unsigned badbits = 0;
-      auto scatter = [&](int q, float r, const float *erow) {
-        if (!(r > 0.0f) || !a.learning) return;
-        const int term = __ldg(a.term_id + b + 32 * q + lane);
-        double *srow = a.stats + (size_t)(term - 1) * K + warp * CPW;
-#pragma unroll
-        for (int c = 0; c < CPW; c++)
-          if (warp * CPW + c < K) atomicAdd(srow + c, (double)(r * theta_w[c] * erow[c]));
-      };
       {
         float r[RREG];
 #pragma unroll
@@ -273,10 +301,6 @@ __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArg
         for (int c = 0; c < CPW; c++) {
 #pragma unroll
           for (int q = 0; q < RREG; q++) s[c] = fmaf(r[q], e[q][c], s[c]);
-        }
-        if (last) {
-#pragma unroll
-          for (int q = 0; q < RREG; q++) scatter(q, r[q], e[q]);
         }
       }
       for (int q = RREG; q < nslots; q++) {
@@ -294,7 +318,6 @@ __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArg
           tmp[c] = __uint_as_float(w32[c]);
           s[c] = fmaf(r, tmp[c], s[c]);
         }
-        if (last) scatter(q, r, tmp);
       }
       // (4) S_c to the owner lane
       float S_f;
@@ -391,6 +414,10 @@ __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArg
         }
       }
     }
+    // statistics scatter of the last sweep, one warp per row (see estep2_scatter_stats); r and theta
+    // stay in shared memory until the barrier at the top of the document loop
+    if (a.learning)
+      estep2f_scatter_stats(a.term_id + b, a.E, a.e_stride, a.stats, K, r_s, theta_s, n, KS, warp, NW, lane);
   }
   if (owner && ss_acc != 0.0) atomicAdd(a.alpha_ss + col, ss_acc);
   if (rt > 0) {

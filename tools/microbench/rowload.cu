@@ -41,6 +41,26 @@ __global__ void __launch_bounds__(256, 1) k(const double *__restrict__ E, const 
 #pragma unroll
         for (int i = 0; i < 13; i++) acc += v[i].x + v[i].y;
       }
+    } else if (MODE == 4) {
+      // A2: as A, but 6 x 256-bit + 1 x 128-bit loads per lane (the slice starts 32-byte aligned for
+      // even warps, 16 bytes off for odd ones)
+      for (int q = 0; q < ROWS / 32; q++) {
+        const double *src = E + (size_t)__ldg(rl + 32 * q + lane) * ROW + warp * 26;
+        double v[26];
+        const int head = (warp & 1) ? 2 : 0;  // doubles before the first 32-byte boundary
+        if (head) {
+          asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[24]), "=d"(v[25]) : "l"(src));
+        } else {
+          asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(v[24]), "=d"(v[25]) : "l"(src + 24));
+        }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+          asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                       : "=d"(v[4 * i]), "=d"(v[4 * i + 1]), "=d"(v[4 * i + 2]), "=d"(v[4 * i + 3])
+                       : "l"(src + head + 4 * i));
+#pragma unroll
+        for (int i = 0; i < 26; i++) acc += v[i];
+      }
     } else if (MODE == 1) {
       for (int r0 = warp; r0 < ROWS; r0 += 8 * NW) {
         double v[8][7];
@@ -197,6 +217,7 @@ int main() {
     for (int grid : {148, 1}) {
       const size_t big = 200 * 1024;  // same carve-out as the E-step kernel: L1 is small
       run<0>("A lanes=rows, 13 x LDG.128", E, rows, grid, ndocs, big);
+      run<4>("A2 lanes=rows, 6 x LDG.256 + 1", E, rows, grid, ndocs, big);
       run<1>("B warp per row, LDG.64 x7, 8 rows", E, rows, grid, ndocs, big);
       run<2>("C warp per row, LDG.128 x4, 8 rows", E, rows, grid, ndocs, big);
       run<3>("D TMA bulk rows, 32 per phase", E, rows, grid, ndocs, big);
