@@ -323,7 +323,7 @@ def main():
                          "frac": ach / hbm,
                          "traffic": measured_traffic(args.workload, world) if args.scale == 1.0 else None,
                          "peak_source": how,
-                         "kernel": "estep2_kernel<8,26,2,8> (+ estep_kernel<8,26> for documents above 192 rows)"
+                         "kernel": "estep2_kernel<8,26,2,8> (+ estep_kernel<8,26> for documents above 320 rows)"
                          if K == 200 else "estep2_kernel / estep_kernel",
                          "algorithmic_bytes_per_launch": B,
                          "note": "binding resource is the FP64 pipe, see fp64"},
