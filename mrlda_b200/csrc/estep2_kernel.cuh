@@ -184,6 +184,59 @@ static __device__ __noinline__ void estep2_scatter_stats(const int32_t *term_id,
   }
 }
 
+// Exact log-space redo (updatePhi as written, DocumentMapper.java:402-429) of the rows whose norm
+// underflowed in the linear-space form, by one warp.  Returns the warp lane's share of
+// likelihoodPhi on the last sweep.  Rare (no row of the BASELINE configurations takes it), so it is
+// kept out of line and out of the sweep loop's register allocation.
+template <int CL, int KS>
+static __device__ __noinline__ double estep2_slow_rows(const int32_t *term_id, const int32_t *count,
+                                                       const double *logbeta, double *stats,
+                                                       int *slow_rows, double *gam_s, double *gextra_s,
+                                                       const int K, const int nslots,
+                                                       const unsigned badbits, const int lane,
+                                                       const int crank, const bool last) {
+  namespace cg = cooperative_groups;
+  auto gamma_of = [&](int k) -> double {  // gamma_k lives in the CTA that owns topic k
+    if constexpr (CL > 1)
+      return cg::this_cluster().map_shared_rank(gam_s, k / KS)[k % KS];
+    else
+      return gam_s[k];
+  };
+  double lik = 0.0;
+  for (int q = 0; q < nslots; q++) {
+    unsigned m = __ballot_sync(0xffffffffu, (badbits >> q) & 1u);
+    while (m) {
+      const int l2 = __ffs(m) - 1;
+      m &= m - 1;
+      const int z = 32 * q + l2;
+      const int term = __ldg(term_id + z);
+      const double nw_ = (double)__ldg(count + z);
+      const double *lb = logbeta + (size_t)(term - 1) * K;
+      double mx = -INFINITY;
+      for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gamma_of(k)));
+      mx = warp_max(mx);
+      double sum = 0.0;
+      for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gamma_of(k)) - mx);
+      sum = warp_sum(sum);
+      const double lsum = log(sum);
+      for (int k = lane; k < K; k += 32) {
+        if (k / KS != crank) continue;  // contributions go to the CTA that owns topic k
+        double lphi = lb[k] + digamma_fast(gamma_of(k)) - mx - lsum;
+        double c = nw_ * exp(lphi);
+        if (c > 0.0) {
+          gextra_s[k - crank * KS] += c;  // one warp, distinct k per lane: no race
+          if (last) {
+            lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
+            if (stats) atomicAdd(stats + (size_t)(term - 1) * K + k, c);
+          }
+        }
+      }
+      if (lane == 0 && crank == 0) atomicAdd(slow_rows, 1);
+    }
+  }
+  return lik;
+}
+
 template <int NW, int CPW, int RREG, int WPS, int CL, bool LAST>
 __device__ __forceinline__ void estep2_sweep(
     const EstepArgs &a, double (&e)[RREG][CPW], const double *es, double *part, const double *cnt_s,
@@ -636,45 +689,9 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         if (mycol >= 0) gam_s[lcol] = owner ? gam : 1.0;
         csync();
         if (tid == 0) meta_s[1] = 0;
-        if (warp == 0) {
-          auto gamma_of = [&](int k) -> double {  // gamma_k lives in the CTA that owns topic k
-            if constexpr (CL > 1)
-              return cg::this_cluster().map_shared_rank(gam_s, k / KS)[k % KS];
-            else
-              return gam_s[k];
-          };
-          for (int q = 0; q < nslots; q++) {
-            unsigned m = __ballot_sync(0xffffffffu, (badbits >> q) & 1u);
-            while (m) {
-              const int l2 = __ffs(m) - 1;
-              m &= m - 1;
-              const int64_t z = b + 32 * q + l2;
-              const int term = __ldg(a.term_id + z);
-              const double nw_ = (double)__ldg(a.count + z);
-              const double *lb = a.logbeta + (size_t)(term - 1) * K;
-              double mx = -INFINITY;
-              for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gamma_of(k)));
-              mx = warp_max(mx);
-              double sum = 0.0;
-              for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gamma_of(k)) - mx);
-              sum = warp_sum(sum);
-              const double lsum = log(sum);
-              for (int k = lane; k < K; k += 32) {
-                if (k / KS != crank) continue;  // contributions go to the CTA that owns topic k
-                double lphi = lb[k] + digamma_fast(gamma_of(k)) - mx - lsum;
-                double c = nw_ * exp(lphi);
-                if (c > 0.0) {
-                  gextra_s[k - crank * KS] += c;  // one warp, distinct k per lane: no race
-                  if (last) {
-                    lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
-                    if (a.learning) atomicAdd(a.stats + (size_t)(term - 1) * K + k, c);
-                  }
-                }
-              }
-              if (lane == 0 && crank == 0) atomicAdd(a.slow_rows, 1);
-            }
-          }
-        }
+        if (warp == 0)
+          lik += estep2_slow_rows<CL, KS>(a.term_id + b, a.count + b, a.logbeta, a.learning ? a.stats : nullptr,
+                                          a.slow_rows, gam_s, gextra_s, K, nslots, badbits, lane, crank, last);
         csync();
       }
       if (!last) {
