@@ -145,6 +145,45 @@ __host__ __device__ constexpr size_t estep2_smem_bytes(int rsm, int cap_rows) {
                            + 96);                        // reductions + doc meta
 }
 
+// One thread's CPW-column slice of an E row -> registers.  Lanes hold different rows, so every
+// warp-wide load touches 32 distinct lines and the load phase is bound by the number of load
+// instructions (tools/microbench/rowload.cu: 13 x LDG.128 per slice 10 B/clk/SM, 6 x LDG.256 + 1 x
+// LDG.128 16 B/clk/SM).  mode 0: 128-bit loads only (row stride not a multiple of 32 bytes);
+// mode 1: the slice starts on a 32-byte boundary; mode 2: it starts 16 bytes past one.
+__device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c, double &d) {
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+template <int CPW>
+__device__ __forceinline__ void estep2_load_slice(const double *src, const int mode, double (&v)[CPW]) {
+  if (mode == 0) {
+#pragma unroll
+    for (int i = 0; i < CPW / 2; i++) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(src) + i);
+      v[2 * i] = t.x;
+      v[2 * i + 1] = t.y;
+    }
+  } else if (mode == 1) {
+#pragma unroll
+    for (int c = 0; c + 4 <= CPW; c += 4) ldg256(src + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+    if constexpr (CPW % 4 != 0) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(src + CPW - 2));
+      v[CPW - 2] = t.x;
+      v[CPW - 1] = t.y;
+    }
+  } else {
+    const double2 h = __ldg(reinterpret_cast<const double2 *>(src));
+    v[0] = h.x;
+    v[1] = h.y;
+#pragma unroll
+    for (int c = 2; c + 4 <= CPW; c += 4) ldg256(src + c, v[c], v[c + 1], v[c + 2], v[c + 3]);
+    if constexpr ((CPW - 2) % 4 != 0) {
+      const double2 t = __ldg(reinterpret_cast<const double2 *>(src + CPW - 2));
+      v[CPW - 2] = t.x;
+      v[CPW - 1] = t.y;
+    }
+  }
+}
+
 // Statistics scatter of the last sweep: n_w phi_wk = r_w theta_k E_wk (DocumentMapper.java:315-329).
 // One warp per row, lanes across the CTA's columns, so that both the re-read of the E row (L2) and
 // the atomics are contiguous; the tile's own layout (lanes = rows) would spread every warp-wide
@@ -498,6 +537,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
     }
   }
   const int gwarp = crank * NW + warp;
+  const int ldmode = (a.e_stride & 3) ? 0 : (((gwarp * CPW) & 3) ? 2 : 1);  // see estep2_load_slice
   const int lcol = warp * CPW + mycol;   // column index inside this CTA
   const int col = gwarp * CPW + mycol;   // topic
   const bool owner = mycol >= 0 && col < K;
@@ -541,14 +581,8 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
     for (int q = 0; q < RREG; q++) {
       const int row = 32 * q + lane;
       if (row < n) {
-        const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW);
-#pragma unroll
-        for (int i = 0; i < HALF; i++) {
-          double2 v = __ldg(src + i);
-          e[q][2 * i] = v.x;
-          e[q][2 * i + 1] = v.y;
-        }
+        estep2_load_slice<CPW>(a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW,
+                               ldmode, e[q]);
       } else {
 #pragma unroll
         for (int c = 0; c < CPW; c++) e[q][c] = 0.0;
@@ -566,19 +600,17 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         for (int c = 0; c < T2; c++) tp[c] = 0.0;
       }
       if (row < n) {
-        const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW);
+        double v[CPW];
+        estep2_load_slice<CPW>(a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + gwarp * CPW,
+                               ldmode, v);
 #pragma unroll
-        for (int i = 0; i < HALF; i++) {
-          const double2 v = __ldg(src + i);
-          if (2 * i < TC) {
-            w32[4 * i] = (uint32_t)__double2loint(v.x);
-            w32[4 * i + 1] = (uint32_t)__double2hiint(v.x);
-            w32[4 * i + 2] = (uint32_t)__double2loint(v.y);
-            w32[4 * i + 3] = (uint32_t)__double2hiint(v.y);
-          } else if constexpr (T2 > 0) {
-            *reinterpret_cast<double2 *>(tp + (2 * i - TC)) = v;
-          }
+        for (int c = 0; c < TC; c++) {
+          w32[2 * c] = (uint32_t)__double2loint(v[c]);
+          w32[2 * c + 1] = (uint32_t)__double2hiint(v[c]);
+        }
+        if constexpr (T2 > 0) {
+#pragma unroll
+          for (int c = 0; c < T2; c += 2) *reinterpret_cast<double2 *>(tp + c) = make_double2(v[TC + c], v[TC + c + 1]);
         }
       }
       tmem_st_words<TW>(tbase + (uint32_t)(q - RREG) * TW, w32);
