@@ -276,6 +276,64 @@ static __device__ __noinline__ double estep2_slow_rows(const int32_t *term_id, c
   return lik;
 }
 
+// Document epilogue (DocumentMapper.java:244-259,342-346): final gamma, the document's ELBO term
+// into the job counter, and the owner lane's alpha sufficient statistic (returned).  Runs once per
+// document and is kept out of line, away from the sweep loop's register allocation.
+template <int NW, int CL>
+static __device__ __noinline__ double estep2_epilogue(const bool owner, const double theta_c, const double S_c,
+                                                      const double alpha_c, const double gam, double lik,
+                                                      double *gextra, double *gamma_out, double *red_s,
+                                                      const double lik_alpha, unsigned long long *ll_counter,
+                                                      const int warp, const int lane, const int crank) {
+  namespace cg = cooperative_groups;
+  double g_new = 1.0, lg = 0.0;
+  if (owner) {
+    const double add = theta_c * S_c;
+    g_new = alpha_c + add;
+    if (gextra) {
+      g_new += *gextra;
+      *gextra = 0.0;
+    }
+    if (add != 0.0) lik -= digamma_fast(gam) * add;
+    lg = lgamma(g_new);
+    *gamma_out = g_new;
+  }
+  double sg = warp_sum(owner ? g_new : 0.0);
+  lg = warp_sum(lg);
+  lik = warp_sum(lik);
+  if (lane == 0) {
+    red_s[warp] = sg;
+    red_s[16 + warp] = lg;
+    red_s[32 + warp] = lik;
+  }
+  if constexpr (CL > 1)
+    cg::this_cluster().sync();
+  else
+    __syncthreads();
+  double tg = 0.0, tl = 0.0, tk = 0.0;
+#pragma unroll
+  for (int r = 0; r < CL; r++) {
+    const double *rp = red_s;
+    if constexpr (CL > 1) rp = cg::this_cluster().map_shared_rank(red_s, r);
+#pragma unroll
+    for (int w2 = 0; w2 < NW; w2++) {
+      tg += rp[w2];
+      tl += rp[16 + w2];
+      tk += rp[32 + w2];
+    }
+  }
+  if constexpr (CL > 1)
+    cg::this_cluster().sync();  // red_s is rewritten by the next document
+  else
+    __syncthreads();
+  if (warp == 0 && lane == 0 && crank == 0) {
+    double ll = lik_alpha + (tl - lgamma(tg)) + tk;
+    long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
+    atomicAdd(ll_counter, (unsigned long long)c);
+  }
+  return owner ? digamma_literal(g_new) - digamma_literal(tg) : 0.0;
+}
+
 template <int NW, int CPW, int RREG, int WPS, int CL, bool LAST>
 __device__ __forceinline__ void estep2_sweep(
     const EstepArgs &a, double (&e)[RREG][CPW], const double *es, double *part, const double *cnt_s,
@@ -737,52 +795,9 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         }
       } else {
         // ---- document epilogue (DocumentMapper.java:244-259,342-346) ----
-        double g_new = 1.0, lg = 0.0;
-        if (owner) {
-          const double add = theta_c * S_c;
-          g_new = alpha_c + add;
-          if (anybad) {
-            g_new += gextra_s[lcol];
-            gextra_s[lcol] = 0.0;
-          }
-          if (add != 0.0) lik -= digamma_fast(gam) * add;
-          lg = lgamma(g_new);
-          a.gamma[(size_t)d * K + col] = g_new;
-        }
-        double sg = warp_sum(owner ? g_new : 0.0);
-        lg = warp_sum(lg);
-        lik = warp_sum(lik);
-        if (lane == 0) {
-          red_s[warp] = sg;
-          red_s[16 + warp] = lg;
-          red_s[32 + warp] = lik;
-        }
-        if constexpr (CL > 1)
-          cg::this_cluster().sync();
-        else
-          __syncthreads();
-        double tg = 0.0, tl = 0.0, tk = 0.0;
-#pragma unroll
-        for (int r = 0; r < CL; r++) {
-          const double *rp = red_s;
-          if constexpr (CL > 1) rp = cg::this_cluster().map_shared_rank(red_s, r);
-#pragma unroll
-          for (int w2 = 0; w2 < NW; w2++) {
-            tg += rp[w2];
-            tl += rp[16 + w2];
-            tk += rp[32 + w2];
-          }
-        }
-        if constexpr (CL > 1)
-          cg::this_cluster().sync();  // red_s is rewritten by the next document
-        else
-          __syncthreads();
-        if (owner) ss_acc += digamma_literal(g_new) - digamma_literal(tg);
-        if (tid == 0 && crank == 0) {
-          double ll = lik_alpha + (tl - lgamma(tg)) + tk;
-          long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
-          atomicAdd(a.ll_counter, (unsigned long long)c);
-        }
+        ss_acc += estep2_epilogue<NW, CL>(owner, theta_c, S_c, alpha_c, gam, lik, anybad ? gextra_s + lcol : nullptr,
+                                          owner ? a.gamma + (size_t)d * K + col : nullptr, red_s, lik_alpha,
+                                          a.ll_counter, warp, lane, crank);
 #ifdef MRLDA_PHASE_TIMING
         t_doc3 = clock64();
 #endif
