@@ -97,7 +97,7 @@ static __device__ __noinline__ void estep2f_scatter_stats(const int32_t *term_id
 
 template <int NW, int CPW, int RREG>
 __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArgs a) {
-  constexpr int HALF = CPW / 2, KS = NW * CPW, TS = estep2f_tmem_stride(CPW);
+  constexpr int KS = NW * CPW, TS = estep2f_tmem_stride(CPW);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArg
   }
   if (tid == 0) meta_s[1] = 0;
   float *theta_w = theta_s + warp * CPW;
+  const int ldmode = (a.e_stride & 3) ? 0 : (((warp * CPW) & 3) ? 2 : 1);  // see estep2_load_slice
 
   for (;;) {
     __syncthreads();
@@ -172,14 +173,11 @@ __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArg
     for (int q = 0; q < RREG; q++) {
       const int row = 32 * q + lane;
       if (row < n) {
-        const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+        double v[CPW];
+        estep2_load_slice<CPW>(a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW,
+                               ldmode, v);
 #pragma unroll
-        for (int i = 0; i < HALF; i++) {
-          const double2 v = __ldg(src + i);
-          e[q][2 * i] = (float)v.x;
-          e[q][2 * i + 1] = (float)v.y;
-        }
+        for (int c = 0; c < CPW; c++) e[q][c] = (float)v[c];
       } else {
 #pragma unroll
         for (int c = 0; c < CPW; c++) e[q][c] = 0.0f;
@@ -191,14 +189,11 @@ __global__ void __launch_bounds__(NW * 32, 8 / NW) estep2f_kernel(const EstepArg
 #pragma unroll
       for (int i = 0; i < TS; i++) w32[i] = 0u;
       if (row < n) {
-        const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW);
+        double v[CPW];
+        estep2_load_slice<CPW>(a.E + (size_t)(__ldg(a.term_id + b + row) - 1) * a.e_stride + warp * CPW,
+                               ldmode, v);
 #pragma unroll
-        for (int i = 0; i < HALF; i++) {
-          const double2 v = __ldg(src + i);
-          w32[2 * i] = __float_as_uint((float)v.x);
-          w32[2 * i + 1] = __float_as_uint((float)v.y);
-        }
+        for (int c = 0; c < CPW; c++) w32[c] = __float_as_uint((float)v[c]);
       }
       TmemVec<TS>::st(tbase + (uint32_t)(q - RREG) * TS, w32);
     }
