@@ -733,26 +733,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
       // document leaves it free, else reduce-scatter in registers
       double S_c;
-      if (a.rs_smem && rsm > 0 && nslots < RREG + rt + rsm) {
-        double *scr = es + ((size_t)(rsm - 1) * NW + warp) * 32 * CPW;
-#pragma unroll
-        for (int c = 0; c < CPW; c++) scr[c * 32 + lane] = s[c];
-        __syncwarp();
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        if (lane < CPW) {
-          const double *colp = scr + lane * 32;
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            double2 v = *reinterpret_cast<const double2 *>(colp + 2 * ((i + lane) & 15));
-            double2 u = *reinterpret_cast<const double2 *>(colp + 2 * ((i + 1 + lane) & 15));
-            a0 += v.x;
-            a1 += v.y;
-            a2 += u.x;
-            a3 += u.y;
-          }
-        }
-        S_c = (a0 + a1) + (a2 + a3);
-      } else {
+      {
         int base = 0, cnt = CPW;
         reduce_scatter<CPW, 16, 1, CPW>(s, lane, base, cnt);
         S_c = __shfl_sync(0xffffffffu, s[0], rs_src);

@@ -63,7 +63,7 @@ struct EstepArgs {
   int learning;
   int cap_rows;  // tile capacity in rows (multiple of RPB)
   int tmem_slots;  // register-stationary kernel: slots per thread kept in Tensor Memory
-  int rs_smem;   // register-stationary kernel: transpose S through shared memory (1) or shuffles (0)
+  int rs_smem;   // unused (kept so that the argument block's layout does not change)
 };
 
 #define MRLDA_NORM_TINY 1e-200

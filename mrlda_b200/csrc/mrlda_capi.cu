@@ -1103,13 +1103,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.slow_rows = ctx->d_work + 1;
   a.phase_cycles = ctx->d_phase;
   a.tmem_slots = 0;
-  {
-    // profiling aid: 1 = transpose S through a spare shared-memory slot instead of the shuffle
-    // reduce-scatter (measured slower: 1100 vs 700 cycles per sweep).  The branch stays in the kernel:
-    // removing it changed ptxas' register allocation and cost 9.5 % (A/B measured on one box).
-    const char *rs = getenv("MRLDA_ESTEP2_RS");
-    a.rs_smem = rs ? atoi(rs) : 0;
-  }
+  a.rs_smem = 0;  // unused (the shared-memory transpose of S was measured slower and removed)
   a.K = K;
   a.sweeps = ctx->cfg.sweep_cap - 1;
   a.use_stored_gamma = (ctx->gamma_valid && !ctx->cfg.random_start) ? 1 : 0;
