@@ -9,15 +9,15 @@
 //     rows l, l+32, l+64, ... ("slots").  Thread (w,l) therefore owns the E elements
 //     (row 32q+l, columns of warp w) for every slot q, and nobody else ever touches them.
 //   * The first RREG slots live in REGISTERS for all 99 sweeps (the register file, 256 KB, is the
-//     largest on-chip memory of the SM); further slots live in a thread-private region of shared
-//     memory.  The hot loop reads no shared E data for documents of up to 32*RREG rows.
+//     largest on-chip memory of the SM); the next slots live in Tensor Memory (thread-private
+//     tcgen05.st / tcgen05.ld, no MMA), the rest in a thread-private region of shared memory.
 //   * Per sweep: (1) the lane that owns a column computes theta_c = exp(digamma(gamma_c)) and the
 //     warp broadcasts its CPW thetas; (2) every thread forms the partial dot products of its rows
 //     over its warp's columns and publishes them; CTA barrier; (3a) one thread per row sums the NW
 //     partials (norm_w) and publishes r_w = n_w / norm_w; CTA barrier; (3b) every thread
 //     accumulates S_c += r_w E_wc over its rows; (4) the per-lane S vectors of a warp are
-//     transposed through shared memory (or reduce-scattered in registers) so that S_c lands in the
-//     lane that owns column c, which updates gamma_c.  gamma, alpha and the alpha sufficient
+//     reduce-scattered in registers (shuffles) so that S_c lands in the lane that owns column c,
+//     which updates gamma_c.  gamma, alpha and the alpha sufficient
 //     statistics stay in the owner lane's registers.
 //   * CL > 1: a thread-block cluster of CL CTAs (one per SM) owns the document; the topic split
 //     continues across the CTAs (CTA r, warp w owns columns [(r*NW+w)*CPW, +CPW)), so K up to
@@ -26,6 +26,9 @@
 //   * WPS = warps per SM the variant is compiled for: 8 (255 registers per thread, most of the tile
 //     in registers) or 16 (128 registers per thread, more of the tile in shared memory, twice the
 //     warps to hide the FP64 / shared-memory latencies of the serial phases).
+//   * Code that runs once per document or almost never — the statistics scatter, the epilogue, the
+//     log-space slow path — is kept out of line (__noinline__): the sweep loop sits at the register
+//     limit and ptxas' allocation for it flips (±9 % run time) with anything inlined next to it.
 //   * Work is perfectly balanced across warps (every warp walks all rows); the only idle lanes are
 //     those of the last, partially filled slot.
 #pragma once
