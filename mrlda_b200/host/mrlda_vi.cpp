@@ -52,6 +52,7 @@ void info(const std::string &s) { printf("INFO  VariationalInference: %s\n", s.c
           " -randomstart           start gamma from random point every iteration\n"
           " -reducer <int>         number of reducers (accepted, ignored)\n"
           " -symmetricalpha        symmetric topic Dirichlet prior\n"
+          " -truncatebeta <int>    parsed and unused, as in the reference (VariationalInferenceOptions.java:116-120)\n"
           " -term <int>            number of terms\n"
           " -test <path>           run program in inference mode, i.e. test held-out likelihood\n"
           " -topic <int>           number of topics\n"

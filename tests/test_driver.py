@@ -123,16 +123,3 @@ def test_informed_prior_option(tmp_path, oracle):
     dl, nm, pr = seqfile.read_beta(out + "beta-2", K, V)
     s = ref["present"].astype(bool)
     assert np.array_equal(nm, ref["normaliser"]) and rel_err(dl[s], ref["digamma_lambda"][s]) < 1e-9
-
-
-def test_option_errors_print_help_and_exit_zero():
-    """The reference logs the parse error, prints the usage and exits 0 (VIO.java:251-266)."""
-    for args in (["-output", "x", "-term", "5", "-topic", "2"],                      # -input missing
-                 ["-input", "a", "-output", "b", "-term", "5", "-topic", "0"],      # topics <= 0
-                 ["-input", "a", "-output", "b", "-term", "5", "-topic", "2", "-test", "m"],  # no index
-                 ["-input", "a", "-output", "b", "-term", "5", "-topic", "2", "-modelindex", "3",
-                  "-iteration", "3"],                                                 # index >= iteration
-                 ["-input", "a", "-output", "b", "-term", "5", "-topic", "2", "-modelindex", "1",
-                  "-symmetricalpha"]):                                               # symmetric + resume
-        p = subprocess.run([DRIVER, *args], capture_output=True, text=True, timeout=60)
-        assert p.returncode == 0 and "usage: cc.mrlda.VariationalInference" in p.stderr
