@@ -256,10 +256,12 @@ class SeqReader {
     if (comp || block)
       throw std::runtime_error(path + ": compressed SequenceFiles are not supported (ParseCorpus "
                                       "writes uncompressed records, ParseCorpus.java:680)");
-    int32_t meta = r.i32();
-    for (int32_t i = 0; i < meta; i++) {
-      r.text();
-      r.text();
+    if (ver >= 6) {  // the metadata block came with version 6 (VERSION_WITH_METADATA)
+      int32_t meta = r.i32();
+      for (int32_t i = 0; i < meta; i++) {
+        r.text();
+        r.text();
+      }
     }
     r.need(16);
     memcpy(sync_, r.p, 16);

@@ -1,0 +1,148 @@
+"""The C++ codecs (mrlda_b200/host/, through libmrlda_seqfile.so) against an independent plain-Python
+implementation of the same published layouts (tests/pyseq.py): files written by one side are read
+by the other, for random corpora, model files and sync-marker placements."""
+import struct
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import pyseq
+from mrlda_b200 import seqfile
+
+INT = "org.apache.hadoop.io.IntWritable"
+DBL = "org.apache.hadoop.io.DoubleWritable"
+DOC = "cc.mrlda.Document"
+PIF = "edu.umd.cloud9.io.pair.PairOfIntFloat"
+HMAP = "edu.umd.cloud9.io.map.HMapIDW"
+
+
+@given(st.integers(min_value=-(2 ** 63), max_value=2 ** 63 - 1))
+def test_vint_round_trip(i):
+    b = pyseq.write_vint(i)
+    v, pos = pyseq.read_vint(b, 0)
+    assert v == i and pos == len(b) and 1 <= len(b) <= 9
+
+
+def test_vint_known_encodings():
+    # WritableUtils.writeVLong: one byte in [-112, 127]; otherwise a length/sign byte and big-endian bytes
+    assert pyseq.write_vint(0) == b"\x00" and pyseq.write_vint(127) == b"\x7f"
+    assert pyseq.write_vint(-112) == b"\x90"
+    assert pyseq.write_vint(128) == b"\x8f\x80"
+    assert pyseq.write_vint(255) == b"\x8f\xff"
+    assert pyseq.write_vint(256) == b"\x8e\x01\x00"
+    assert pyseq.write_vint(-113) == b"\x87\x70"
+
+
+docs_strategy = st.lists(
+    st.tuples(
+        st.integers(min_value=-5, max_value=2 ** 31 - 1),  # document id
+        st.dictionaries(st.integers(min_value=1, max_value=500), st.integers(min_value=1, max_value=10 ** 6),
+                        min_size=1, max_size=60),
+    ), min_size=1, max_size=40)
+
+
+@settings(max_examples=25, deadline=None)
+@given(docs_strategy, st.integers(min_value=0, max_value=5), st.integers(min_value=0, max_value=7))
+def test_corpus_written_by_cpp_is_read_by_python(tmp_path_factory, docs, K, seed):
+    path = str(tmp_path_factory.mktemp("c") / "part-00000")
+    rng = np.random.default_rng(seed)
+    row_ptr = np.cumsum([0] + [len(c) for _, c in docs])
+    term = np.concatenate([np.fromiter(c.keys(), dtype=np.int32) for _, c in docs])
+    cnt = np.concatenate([np.fromiter(c.values(), dtype=np.int32) for _, c in docs])
+    ids = np.array([d for d, _ in docs], dtype=np.int32)
+    gamma = rng.gamma(1.0, size=(len(docs), K)) if K else None
+    seqfile.write_corpus(path, row_ptr, term, cnt, doc_id=ids, gamma=gamma, n_topics=K)
+    kc, vc, _, records, escapes = pyseq.read_file(path)
+    assert (kc, vc) == (INT, DOC) and len(records) == len(docs)
+    total = sum(8 + len(k) + len(v) for k, v in records)
+    assert escapes >= total // 4000  # a sync escape at least every few thousand bytes (SYNC_INTERVAL 2000)
+    for i, (k, v) in enumerate(records):
+        assert struct.unpack(">i", k)[0] == ids[i]
+        content, g = pyseq.parse_document(v)
+        assert content == docs[i][1]
+        if K:
+            assert np.array_equal(np.array(g), gamma[i])
+        else:
+            assert g is None
+
+
+@settings(max_examples=25, deadline=None)
+@given(docs_strategy, st.integers(min_value=0, max_value=4), st.sampled_from([None, 1, 2, 7]))
+def test_corpus_written_by_python_is_read_by_cpp(tmp_path_factory, docs, K, sync_every):
+    path = str(tmp_path_factory.mktemp("p") / "part-00000")
+    rng = np.random.default_rng(len(docs))
+    gamma = rng.gamma(1.0, size=(len(docs), K)) if K else None
+    records = [(struct.pack(">i", d), pyseq.document_bytes(c, gamma[i] if K else None))
+               for i, (d, c) in enumerate(docs)]
+    pyseq.write_file(path, INT, DOC, records, sync=bytes(rng.integers(0, 256, 16, dtype=np.uint8)),
+                     sync_every=sync_every)
+    got = seqfile.read_corpus(path, max(K, 1), 500)
+    assert np.array_equal(got["doc_id"], [d for d, _ in docs])
+    assert np.array_equal(np.diff(got["row_ptr"]), [len(c) for _, c in docs])
+    for i, (_, c) in enumerate(docs):
+        lo, hi = got["row_ptr"][i], got["row_ptr"][i + 1]
+        assert dict(zip(got["term_id"][lo:hi].tolist(), got["count"][lo:hi].tolist())) == c
+    if K:
+        assert np.array_equal(got["gamma"], gamma)
+    else:
+        assert got["gamma"] is None
+
+
+def test_alpha_and_beta_files_cross_check(tmp_path):
+    rng = np.random.default_rng(3)
+    K, V = 7, 23
+    alpha = rng.gamma(1.0, size=K)
+    seqfile.write_alpha(str(tmp_path / "alpha"), alpha)
+    kc, vc, _, records, _ = pyseq.read_file(str(tmp_path / "alpha"))
+    assert (kc, vc) == (INT, DBL)
+    assert [struct.unpack(">i", k)[0] for k, _ in records] == list(range(1, K + 1))  # VI.java:549-558
+    assert np.array_equal([struct.unpack(">d", v)[0] for _, v in records], alpha)
+    # and the other way round, in a shuffled record order (importAlpha indexes by key, VI.java:521-540)
+    order = rng.permutation(K)
+    pyseq.write_file(str(tmp_path / "alpha2"), INT, DBL,
+                     [(struct.pack(">i", int(i) + 1), struct.pack(">d", alpha[i])) for i in order])
+    assert np.array_equal(seqfile.read_alpha(str(tmp_path / "alpha2"), K), alpha)
+
+    dl = rng.normal(size=(V, K))
+    nm = rng.normal(size=K).astype(np.float32)
+    present = (rng.random(V) < 0.7).astype(np.uint8)
+    seqfile.write_beta(str(tmp_path / "beta"), dl, nm, present)
+    kc, vc, _, records, _ = pyseq.read_file(str(tmp_path / "beta"))
+    assert (kc, vc) == (PIF, HMAP) and len(records) == K  # one record per topic (TermReducer.java:232-235)
+    seen = np.flatnonzero(present) + 1
+    for k, (key, val) in enumerate(records):
+        topic, norm = struct.unpack(">if", key)
+        assert topic == k + 1 and np.float32(norm) == nm[k]
+        (n,) = struct.unpack_from(">i", val, 0)
+        assert n == len(seen) and len(val) == 4 + 12 * n
+        for j in range(n):
+            term, x = struct.unpack_from(">id", val, 4 + 12 * j)
+            assert term == seen[j] and x == dl[term - 1, k]
+    # python-written beta with the terms of each topic in a different order
+    recs = []
+    for k in range(K):
+        terms = rng.permutation(seen)
+        val = struct.pack(">i", len(terms)) + b"".join(struct.pack(">id", int(t), dl[t - 1, k]) for t in terms)
+        recs.append((struct.pack(">if", k + 1, float(nm[k])), val))
+    pyseq.write_file(str(tmp_path / "beta2"), PIF, HMAP, recs, sync_every=3)
+    dl2, nm2, pr2 = seqfile.read_beta(str(tmp_path / "beta2"), K, V)
+    assert np.array_equal(pr2, present) and np.array_equal(nm2, nm)
+    assert np.array_equal(dl2[present.astype(bool)], dl[present.astype(bool)])
+
+
+def test_cpp_reader_rejects_damaged_files(tmp_path):
+    good = [(struct.pack(">i", 1), pyseq.document_bytes({1: 2}, None))]
+    p = str(tmp_path / "x")
+    pyseq.write_file(p, INT, DOC, good, version=7)  # a version this reader does not know
+    with pytest.raises(seqfile.SeqFileError):
+        seqfile.read_corpus(p, 1, 10)
+    pyseq.write_file(p, INT, DOC, good, version=5)  # version 5: same header without the metadata block
+    assert seqfile.read_corpus(p, 1, 10)["count"].tolist() == [2]
+    pyseq.write_file(p, INT, DBL, good)  # wrong value class
+    with pytest.raises(seqfile.SeqFileError):
+        seqfile.read_corpus(p, 1, 10)
+    pyseq.write_file(p, INT, DOC, good)
+    open(p, "ab").write(b"\x00\x00\x00\x20\x00\x00")  # truncated record
+    with pytest.raises(seqfile.SeqFileError):
+        seqfile.read_corpus(p, 1, 10)
