@@ -146,3 +146,24 @@ def test_cpp_reader_rejects_damaged_files(tmp_path):
     open(p, "ab").write(b"\x00\x00\x00\x20\x00\x00")  # truncated record
     with pytest.raises(seqfile.SeqFileError):
         seqfile.read_corpus(p, 1, 10)
+
+
+def test_term_index_and_eta_files_cross_check(tmp_path):
+    terms = ["alpha", "bêta", "γάμμα", "x" * 300]  # a Text longer than 127 bytes needs a multi-byte vint
+    seqfile.write_term_index(str(tmp_path / "term"), terms)
+    kc, vc, _, records, _ = pyseq.read_file(str(tmp_path / "term"))
+    assert (kc, vc) == (INT, "org.apache.hadoop.io.Text")
+    for i, (k, v) in enumerate(records):
+        assert struct.unpack(">i", k)[0] == i + 1  # ids 1..V in index order (ParseCorpus.java:484-487)
+        n, pos = pyseq.read_vint(v, 0)
+        assert v[pos:pos + n].decode("utf-8") == terms[i] and pos + n == len(v)
+
+    seqfile.write_eta(str(tmp_path / "eta"), 3, [1, 1, 3], [5, 9, 2])
+    kc, vc, _, records, _ = pyseq.read_file(str(tmp_path / "eta"))
+    assert (kc, vc) == (INT, "edu.umd.cloud9.io.array.ArrayListOfIntsWritable")
+    got = {}
+    for k, v in records:
+        (n,) = struct.unpack_from(">i", v, 0)
+        assert len(v) == 4 + 4 * n
+        got[struct.unpack(">i", k)[0]] = list(struct.unpack_from(">%di" % n, v, 4))
+    assert got == {1: [5, 9], 2: [], 3: [2]}  # one record per topic (InformedPrior.java:139-170)
