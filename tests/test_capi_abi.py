@@ -53,3 +53,26 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not bad.search(text), f"{f} uses the oracle"
+
+
+def test_argument_errors_are_codes_not_crashes(capi):
+    """Argument validation happens before any CUDA call and answers with MRLDA_EINVAL plus a message
+    (the reference's Preconditions.checkArgument); null handles are tolerated everywhere."""
+    lib = capi.load()
+    lib.mrlda_last_error.restype = ctypes.c_char_p
+    lib.mrlda_last_error.argtypes = [ctypes.c_void_p]
+    h = ctypes.c_void_p()
+    assert lib.mrlda_create(None, ctypes.byref(h)) == -1 and not h.value
+    for field, bad in (("n_topics", 0), ("n_terms", -3), ("sweep_cap", 1), ("world_size", 0), ("rank", 5),
+                       ("eta", 0.0)):
+        cfg = capi.default_config()
+        cfg.n_topics, cfg.n_terms = 4, 10
+        setattr(cfg, field, bad)
+        assert lib.mrlda_create(ctypes.byref(cfg), ctypes.byref(h)) == -1, field
+        assert not h.value and b"invalid config" in lib.mrlda_last_error(None)
+    # a null context: every entry point returns a code (or 0 launches), none dereferences it
+    assert lib.mrlda_e_step(None, None) == -1
+    assert lib.mrlda_m_step(None, None) == -1
+    assert lib.mrlda_iterate(None, None) == -1
+    assert lib.mrlda_kernel_launches(None) == 0
+    lib.mrlda_destroy(None)
