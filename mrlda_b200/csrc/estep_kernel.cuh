@@ -63,7 +63,8 @@ struct EstepArgs {
   int learning;
   int cap_rows;  // tile capacity in rows (multiple of RPB)
   int tmem_slots;  // register-stationary kernel: slots per thread kept in Tensor Memory
-  int rs_smem;   // unused (kept so that the argument block's layout does not change)
+  int group_warps;   // warp-group kernel (estep3): warps per document
+  int smem_batches;  // warp-group kernel (estep3): shared-memory batches per warp
 };
 
 #define MRLDA_NORM_TINY 1e-200

@@ -24,6 +24,7 @@
 
 #include "../../include/mrlda_b200.h"
 #include "estep2f_kernel.cuh"
+#include "estep3_kernel.cuh"
 
 using namespace mrlda;
 
@@ -416,6 +417,7 @@ struct mrlda_ctx {
   const EstepVariant *variant = nullptr;    // general kernel (any document length)
   const Estep2Variant *variant2 = nullptr;  // register-stationary kernel (documents that fit one SM)
   const Estep2fVariant *variant2f = nullptr;  // fp32-mode counterpart of variant2 (same NW, CPW)
+  const Estep3Variant *variant3 = nullptr;  // warp-group kernel (several documents in flight per SM)
   int ES = 0;                               // row stride of E in doubles
   std::vector<int32_t> h_nnz_sorted;        // nnz per document in doc_order (descending)
   int num_sms = 0;
@@ -447,7 +449,7 @@ struct mrlda_ctx {
   // per-iteration
   double *d_alpha_ss = nullptr;   // K
   long long *d_counters = nullptr; // [0] ll counter, [1] n_docs, [2] n_tokens, [3] slow rows
-  int *d_work = nullptr;           // [0] work queue, [1] slow rows
+  int *d_work = nullptr;           // [0] work queue, [1] slow rows, [2..3] estep2, [4..7] estep3 classes
   long long *d_phase = nullptr;    // phase cycle counters (MRLDA_PHASE_TIMING builds)
   double *d_partial = nullptr, *d_colsum = nullptr, *d_alpha_work = nullptr;
   int nslabs = 0, slab = 0;
@@ -531,6 +533,23 @@ static const Estep2Variant *select_variant2(int K) {
       best = nullptr;  // slice too wide at this warp count: try more warps
     }
   }
+  return best;
+}
+
+// Warp-group kernel: narrowest row (L * KPL >= K).  MRLDA_ESTEP_KERNEL=2 (register-stationary
+// kernel of round 1) or =1 (general kernel only) switch it off for A/B runs.
+static const Estep3Variant *select_variant3(int K) {
+  const char *fk = getenv("MRLDA_ESTEP_KERNEL");
+  if (fk && (atoi(fk) == 1 || atoi(fk) == 2)) return nullptr;
+  const Estep3Variant *tabs[] = {g_estep3_variants_L8};
+  const int ns[] = {g_estep3_variants_L8_n};
+  const Estep3Variant *best = nullptr;
+  for (size_t t = 0; t < sizeof(ns) / sizeof(ns[0]); t++)
+    for (int i = 0; i < ns[t]; i++) {
+      const Estep3Variant *v = &tabs[t][i];
+      if (v->L * v->KPL < K) continue;
+      if (!best || v->L * v->KPL < best->L * best->KPL) best = v;
+    }
   return best;
 }
 
@@ -628,6 +647,8 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   ctx->ES = ctx->KS;
   if (ctx->variant2)
     ctx->ES = std::max(ctx->ES, ctx->variant2->CL * ctx->variant2->NW * ctx->variant2->CPW);
+  ctx->variant3 = cfg->fp32_mode ? nullptr : select_variant3(ctx->K);
+  if (ctx->variant3) ctx->ES = std::max(ctx->ES, ctx->variant3->L * ctx->variant3->KPL);
   auto fail = [&](int code) {
     g_global_error = ctx->err;
     mrlda_destroy(ctx);
@@ -666,7 +687,7 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   CKC(cudaMalloc(&ctx->d_present, V));
   CKC(cudaMalloc(&ctx->d_alpha_ss, K * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_counters, 4 * sizeof(long long)));
-  CKC(cudaMalloc(&ctx->d_work, 4 * sizeof(int)));
+  CKC(cudaMalloc(&ctx->d_work, 16 * sizeof(int)));
   CKC(cudaMalloc(&ctx->d_phase, 16 * sizeof(long long)));
   CKC(cudaMemset(ctx->d_phase, 0, 16 * sizeof(long long)));
   ctx->slab = 256;
@@ -1081,7 +1102,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   CK(cudaMemsetAsync(ctx->d_alpha_ss, 0, (size_t)K * sizeof(double), st));
   long long hc[4] = {0, (long long)ctx->D, (long long)ctx->n_tokens, 0};
   CK(cudaMemcpyAsync(ctx->d_counters, hc, sizeof hc, cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(ctx->d_work, 0, 4 * sizeof(int), st));
+  CK(cudaMemsetAsync(ctx->d_work, 0, 16 * sizeof(int), st));
 
   EstepArgs a;
   a.row_ptr = ctx->d_row_ptr;
@@ -1103,7 +1124,8 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.slow_rows = ctx->d_work + 1;
   a.phase_cycles = ctx->d_phase;
   a.tmem_slots = 0;
-  a.rs_smem = 0;  // unused (the shared-memory transpose of S was measured slower and removed)
+  a.group_warps = 0;
+  a.smem_batches = 0;
   a.K = K;
   a.sweeps = ctx->cfg.sweep_cap - 1;
   a.use_stored_gamma = (ctx->gamma_valid && !ctx->cfg.random_start) ? 1 : 0;
@@ -1163,6 +1185,41 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       if (grid2 > 0) CK(v2->prepare(smem2));
     }
   }
+  // Warp-group kernel (estep3): documents are classed by the number of warps they need; class G
+  // (G warps per document, 8/G documents in flight per SM) takes the documents of at most
+  // G * (R + T + M_G) * RPB rows that do not fit class G/2.  One launch per class, longest first.
+  const Estep3Variant *v3 = (use2f || !use2) ? nullptr : ctx->variant3;
+  int cls_begin[5] = {0, 0, 0, 0, 0}, cls_M[4] = {0, 0, 0, 0};
+  size_t cls_smem[4] = {0, 0, 0, 0};
+  if (v3 && ctx->D > 0) {
+    const size_t per = std::min((size_t)233472 - 1024, ctx->smem_optin) & ~(size_t)15;
+    const int rpb = 32 / v3->L;
+    const char *fg = getenv("MRLDA_ESTEP3_GROUPS");  // bit mask of allowed group sizes (profiling aid)
+    const int gmask = fg ? atoi(fg) : 15;
+    bool ok3 = true;
+    cls_begin[4] = (int)ctx->D;
+    for (int ci = 3; ci >= 0; ci--) {  // ci: 0 -> G=8, 1 -> G=4, 2 -> G=2, 3 -> G=1
+      const int G = 8 >> ci;
+      int M = 4;
+      while (M > 0 && v3->smem_bytes(M, G) > per) M--;
+      if (v3->smem_bytes(M, G) > per) ok3 = false;
+      cls_M[ci] = M;
+      cls_smem[ci] = v3->smem_bytes(M, G);
+      const bool enabled = ci == 0 || ((gmask >> (3 - ci)) & 1);
+      const int capG = G * (v3->R + v3->T + M) * rpb;
+      // first document (in descending nnz order) that fits class ci
+      cls_begin[ci] = !enabled ? cls_begin[ci + 1]
+                               : (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), capG,
+                                                        [](int cap, int32_t nn) { return cap >= nn; }) -
+                                       ctx->h_nnz_sorted.begin());
+    }
+    if (ok3) {
+      n_long = cls_begin[0];
+      grid2 = 0;
+    } else {
+      v3 = nullptr;
+    }
+  }
   int c = 1, t = 32, cap = 2;
   size_t smem = 0;
   if (n_long > 0) {
@@ -1170,17 +1227,46 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
     CK(ctx->variant->prepare(smem));
   }
   CK(cudaEventRecord(ctx->ev[1], st));
+  if (v3) {
+    // the general kernel (documents longer than one SM holds) runs beside the class launches
+    const bool fork = n_long > 0 && n_long < (int)ctx->D && !getenv("MRLDA_ESTEP_SERIAL");
+    if (n_long > 0) {
+      cudaStream_t sp = fork ? ctx->stream2 : st;
+      if (fork) CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev[1], 0));
+      a.doc_begin = 0;
+      a.doc_end = n_long;
+      a.work_counter = ctx->d_work;
+      a.cap_rows = cap;
+      int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, n_long);
+      CK(ctx->variant->launch(a, grid, t, cap, sp));
+      ctx->launches++;
+      if (fork) CK(cudaEventRecord(ctx->ev[7], ctx->stream2));
+    }
+    for (int ci = 0; ci < 4; ci++) {
+      const int nd = cls_begin[ci + 1] - cls_begin[ci];
+      if (nd <= 0) continue;
+      const int G = 8 >> ci;
+      a.doc_begin = cls_begin[ci];
+      a.doc_end = cls_begin[ci + 1];
+      a.work_counter = ctx->d_work + 4 + ci;
+      CK(v3->prepare(cls_smem[ci]));
+      const int grid = (int)std::min<int64_t>(ctx->num_sms, ((int64_t)nd + (8 / G) - 1) / (8 / G));
+      CK(v3->launch(a, grid, G, cls_M[ci], cls_smem[ci], st));
+      ctx->launches++;
+    }
+    if (fork) CK(cudaStreamWaitEvent(st, ctx->ev[7], 0));
+  }
   // The two kernels work on disjoint documents and only meet in atomics, so they run on two
   // streams.  A cluster launch cannot use every SM (132 of 148 at cluster size 4): it goes first and
   // the general kernel's persistent CTAs fill the SMs it leaves free, then the rest of the GPU once
   // it drains.  Otherwise the general kernel (the longest documents) goes first and the
   // register-stationary CTAs take over each SM as it runs out of long documents.
-  const bool overlap = n_long > 0 && grid2 > 0 && !getenv("MRLDA_ESTEP_SERIAL");
+  const bool overlap = !v3 && n_long > 0 && grid2 > 0 && !getenv("MRLDA_ESTEP_SERIAL");
   const bool cluster_first = overlap && !use2f && ctx->variant2->CL > 1;
   // the kernel that should start first stays on the main stream (nothing to wait for); the other
   // one goes to the second stream behind the fork event
   if (overlap) CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev[1], 0));
-  for (int pass = 0; pass < 2; pass++) {
+  for (int pass = 0; pass < 2 && !v3; pass++) {
     const bool long_pass = (pass == 0) != cluster_first;
     cudaStream_t sp = (pass == 1 && overlap) ? ctx->stream2 : st;
     if (long_pass && n_long > 0) {
