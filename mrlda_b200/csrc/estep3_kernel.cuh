@@ -4,11 +4,12 @@
 // log-space redo of underflowing rows; reference: DocumentMapper.java:175-350, updatePhi :402-429).
 // What changes is who owns what:
 //
-//   * A CTA is 8 warps on one SM.  A document is owned by a GROUP of G consecutive warps
-//     (G in {1,2,4,8}, a launch parameter), so 8/G documents are in flight per SM and one
-//     document's serial phases (S exchange, exp(digamma), barriers) overlap another document's
-//     DFMA phases on the same FP64 pipes.  Groups synchronise on named barriers (bar.sync id, 32*G)
-//     and pull documents from the work queue independently of each other.
+//   * A CTA is NW warps on one SM (8, 12 or 16: 255, 168 or 128 registers per thread).  A document
+//     is owned by a GROUP of G consecutive warps (G divides NW, a launch parameter), so NW/G
+//     documents are in flight per SM and one document's serial phases (S exchange, exp(digamma),
+//     barriers) overlap another document's DFMA phases on the same FP64 pipes.  Groups
+//     synchronise on named barriers (bar.sync id, 32*G) and pull documents from the work queue
+//     independently of each other.
 //   * Inside a group ROWS are split across warps: warp k owns a contiguous range of row batches.
 //     A batch is RPB = 32/L rows; L lanes share a row, lane j of a row owns the KPL columns
 //     {2(j + L i), 2(j + L i) + 1}, i < KPL/2 (same column interleave as estep_kernel.cuh, so row
@@ -17,9 +18,9 @@
 //     levels at K = 200) and r_w = n_w / norm_w is used by the same lanes right away — no CTA
 //     barrier and no shared-memory exchange per row.  S_c accumulates per lane over the warp's rows.
 //   * A warp's batches live, in this order, in REGISTERS (the first R batches), in TENSOR MEMORY
-//     (the next T = 256 / (2 KPL) batches: thread-private tcgen05.st / tcgen05.ld, no MMA; warps w
-//     and w+4 share a lane quarter and split the 512 columns), and in a thread-private,
-//     lane-interleaved region of SHARED MEMORY (the last M batches).
+//     (the next T batches: thread-private tcgen05.st / tcgen05.ld, no MMA; the NW/4 warps that
+//     share a lane quarter split the 512 columns), and in a thread-private, lane-interleaved
+//     region of SHARED MEMORY (the last M batches).
 //   * Per sweep and warp.  Pass A: theta in registers; partial dot products of every batch (TMEM
 //     batches are fetched in two parts so that one tcgen05.ld is always in flight behind the
 //     DFMAs).  Then the L-lane butterflies and the reciprocals of ALL batches as independent,
@@ -28,6 +29,11 @@
 //     RPB x K partial sums to shared memory as they are (no shuffle reduction), group barrier,
 //     the group's threads own one or two columns each: sum the RPB*G partials,
 //     gamma_c = alpha_c + theta_c S_c, theta_c = exp(digamma(gamma_c)), group barrier.
+//   * The 98 sweeps that are not the last one run in a loop body specialised on the number of
+//     TMEM and shared-memory batches the warp holds (chosen once per document), so the loop is
+//     straight-line code: with two to four warps per scheduler and in-order issue, every branch,
+//     jump table and dependent load in the sweep shows up in the run time.  The last sweep
+//     (likelihood terms, statistics scatter) is generic code.
 //   * Padding rows (a partially filled last batch, unused register batches) hold a copy of the
 //     document's last row with n_w = 0: their norm is a real norm and their r is 0, so the sweep
 //     needs no validity test per row; one integer minimum over the norms' high words per sweep
@@ -41,42 +47,44 @@
 
 namespace mrlda {
 
-template <int L, int KPL, int R>
+template <int L, int KPL, int R, int NW>
 struct Estep3Shape {
   static constexpr int RPB = 32 / L;
   static constexpr int KS = L * KPL;
   static constexpr int HALF = KPL / 2;
-  static constexpr int TW = 2 * KPL;   // 32-bit TMEM columns per batch and lane
-  static constexpr int T = 256 / TW;   // TMEM batches per warp
-  static constexpr int MMAX = 4;       // upper bound of the shared-memory batches per warp
+  static constexpr int TW = 2 * KPL;                   // 32-bit TMEM columns per batch and lane
+  static constexpr int WQ = NW / 4;                    // warps that share a TMEM lane quarter
+  static constexpr int TWORDS = (512 / WQ) / 4 * 4;    // TMEM columns of one warp
+  static constexpr int T = TWORDS / TW;                // TMEM batches per warp
+  static constexpr int MMAX = 3;                       // upper bound of the shared-memory batches per warp
   static constexpr int NBMAX = R + T + MMAX;
-  static constexpr int CA = 16;        // columns of a TMEM batch fetched by the first tcgen05.ld
-  static constexpr int CB = KPL - CA;  // ... and by the second
+  static constexpr int CA = 16;                        // columns of a TMEM batch fetched by the first tcgen05.ld
+  static constexpr int CB = KPL - CA;                  // ... and by the second
+  static constexpr int RA = R > 0 ? R : 1;             // extent of the register-batch array
+  static constexpr int THREADS = NW * 32;
   static_assert(KPL % 2 == 0 && KPL > CA && KPL <= 32, "KPL must be even, in (16, 32]");
   static_assert(L == 1 || L == 2 || L == 4 || L == 8 || L == 16 || L == 32, "L must divide 32");
-  static_assert(T <= 4 && MMAX == 4, "the batch-count dispatch below is written for T, MMAX <= 4");
+  static_assert(NW == 8 || NW == 12 || NW == 16, "NW in {8, 12, 16}");
 };
 
 // shared-memory carve-up (offsets in doubles) for M shared-memory batches per warp, groups of G warps
-template <int L, int KPL, int R>
+template <int L, int KPL, int R, int NW>
 struct Estep3Smem {
-  using S = Estep3Shape<L, KPL, R>;
+  using S = Estep3Shape<L, KPL, R, NW>;
   size_t tile, spart, theta, gam, gextra, alpha, ssacc, cnt, red, meta, total;
-  int capw;  // rows one warp can hold
   __host__ __device__ Estep3Smem(int M, int G) {
-    const int NG = 8 / G;
-    capw = (R + S::T + M) * S::RPB;
+    const int NG = NW / G;
     size_t o = 0;
-    tile = o;   o += (size_t)8 * M * 32 * KPL;
-    spart = o;  o += (size_t)8 * 32 * KPL;    // every lane's S partials: [warp][i][lane] double2
+    tile = o;   o += (size_t)NW * M * 32 * KPL;
+    spart = o;  o += (size_t)NW * 32 * KPL;   // every lane's S partials: [warp][i][lane] double2
     theta = o;  o += (size_t)NG * S::KS;
     gam = o;    o += (size_t)NG * S::KS;
     gextra = o; o += (size_t)NG * S::KS;
     alpha = o;  o += S::KS;
     ssacc = o;  o += S::KS;
-    cnt = o;    o += (size_t)8 * S::NBMAX * S::RPB;  // n_w of every batch slot (0: padding)
-    red = o;    o += 8 * 4;
-    meta = o;   o += 8;  // 16 ints
+    cnt = o;    o += (size_t)NW * S::NBMAX * S::RPB;  // n_w of every batch slot (0: padding)
+    red = o;    o += NW * 4;
+    meta = o;   o += 10;  // 20 ints: [0] TMEM base, [1 + group] document
     total = o * sizeof(double);
   }
 };
@@ -146,204 +154,43 @@ static __device__ __noinline__ double estep3_slow_rows(const int32_t *term_id, c
   return lik;
 }
 
-// ---- pass A pieces: partial dot products ----
-// NT TMEM batches, software pipelined: part A (CA columns) and part B (CB columns) of a batch are
-// separate loads, and the next load is issued before the DFMAs of the part that just arrived.
-template <int L, int KPL, int R, int NT>
-__device__ __forceinline__ void estep3_dots_tmem(const double (&th)[KPL], const uint32_t tbase,
-                                                 double (&pr)[Estep3Shape<L, KPL, R>::NBMAX]) {
-  using S = Estep3Shape<L, KPL, R>;
-  constexpr int CA = S::CA, CB = S::CB, TW = S::TW;
-  if constexpr (NT > 0) {
-    uint32_t wa[2 * CA], wb[2 * CB];
-    tmem_ld_words<2 * CA>(tbase, wa);
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-      tmem_wait_ld();
-      tmem_ld_words<2 * CB>(tbase + (uint32_t)(t * TW + 2 * CA), wb);
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-      for (int c = 0; c < CA; c += 4) {
-        a0 = fma(th[c], estep3_w2d(wa[2 * c], wa[2 * c + 1]), a0);
-        a1 = fma(th[c + 1], estep3_w2d(wa[2 * c + 2], wa[2 * c + 3]), a1);
-        a2 = fma(th[c + 2], estep3_w2d(wa[2 * c + 4], wa[2 * c + 5]), a2);
-        a3 = fma(th[c + 3], estep3_w2d(wa[2 * c + 6], wa[2 * c + 7]), a3);
-      }
-      tmem_wait_ld();
-      if (t + 1 < NT) tmem_ld_words<2 * CA>(tbase + (uint32_t)((t + 1) * TW), wa);
-#pragma unroll
-      for (int c = 0; c < CB; c += 2) {
-        if (c & 2) {
-          a2 = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), a2);
-          a3 = fma(th[CA + c + 1], estep3_w2d(wb[2 * c + 2], wb[2 * c + 3]), a3);
-        } else {
-          a0 = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), a0);
-          a1 = fma(th[CA + c + 1], estep3_w2d(wb[2 * c + 2], wb[2 * c + 3]), a1);
-        }
-      }
-      pr[R + t] = (a0 + a1) + (a2 + a3);
-    }
-  }
-}
-template <int L, int KPL, int R, int NM>
-__device__ __forceinline__ void estep3_dots_smem(const double (&th)[KPL], const double2 *tile2,
-                                                 double (&pr)[Estep3Shape<L, KPL, R>::NBMAX]) {
-  using S = Estep3Shape<L, KPL, R>;
-  constexpr int HALF = S::HALF, T = S::T;
-#pragma unroll
-  for (int m = 0; m < NM; m++) {
-    const double2 *src = tile2 + (size_t)m * HALF * 32;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-#pragma unroll
-    for (int i = 0; i < HALF; i++) {
-      const double2 v = src[(size_t)i * 32];
-      if (i & 1) {
-        a2 = fma(th[2 * i], v.x, a2);
-        a3 = fma(th[2 * i + 1], v.y, a3);
-      } else {
-        a0 = fma(th[2 * i], v.x, a0);
-        a1 = fma(th[2 * i + 1], v.y, a1);
-      }
-    }
-    pr[R + T + m] = (a0 + a1) + (a2 + a3);
-  }
-}
+// Everything a warp needs to walk its batches (built once per kernel).
+template <int L, int KPL, int R, int NW>
+struct Estep3Warp {
+  uint32_t tbase;          // this warp's TMEM slots
+  const double2 *tile2;    // this warp's shared-memory batches (+ lane)
+  const double2 *theta2;   // the group's theta as double2 pairs
+  const double *cnt_w;     // n_w of this warp's batch slots (0 for padding rows)
+  int g, j;                // row of the batch / column group this lane works on
+};
 
-// ---- norms -> r for the first NA batch slots: every step runs over all slots before the next ----
-template <int L, int KPL, int R, int NA>
-__device__ __forceinline__ void estep3_norms_to_r(double (&pr)[Estep3Shape<L, KPL, R>::NBMAX],
-                                                  double (&rr)[Estep3Shape<L, KPL, R>::NBMAX],
-                                                  const double *cnt_w, const int g, int &minhi) {
-  constexpr int RPB = 32 / L;
-#pragma unroll
-  for (int o = 1; o < L; o <<= 1) {
-#pragma unroll
-    for (int bi = 0; bi < NA; bi++) pr[bi] += __shfl_xor_sync(0xffffffffu, pr[bi], o);
-  }
-  double y[NA], t1[NA];
-#pragma unroll
-  for (int bi = 0; bi < NA; bi++) {
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[bi]) : "d"(pr[bi]));
-    minhi = min(minhi, __double2hiint(pr[bi]));
-  }
-#pragma unroll
-  for (int bi = 0; bi < NA; bi++) t1[bi] = fma(-pr[bi], y[bi], 1.0);
-#pragma unroll
-  for (int bi = 0; bi < NA; bi++) y[bi] = fma(y[bi], t1[bi], y[bi]);
-#pragma unroll
-  for (int bi = 0; bi < NA; bi++) t1[bi] = fma(-pr[bi], y[bi], 1.0);
-#pragma unroll
-  for (int bi = 0; bi < NA; bi++) y[bi] = fma(y[bi], t1[bi], y[bi]);
-#pragma unroll
-  for (int bi = 0; bi < NA; bi++) rr[bi] = cnt_w[bi * RPB + g] * y[bi];
-}
-
-// ---- pass B pieces: S_c += r_w E_wc ----
-template <int L, int KPL, int R, int NT, bool LAST>
-__device__ __forceinline__ void estep3_sacc_tmem(const EstepArgs &a, const uint32_t tbase,
-                                                 const double (&rr)[Estep3Shape<L, KPL, R>::NBMAX],
-                                                 double (&s)[KPL], const double2 *theta2,
-                                                 const int64_t zrow0, const int g, const int j) {
-  using S = Estep3Shape<L, KPL, R>;
-  constexpr int CA = S::CA, CB = S::CB, TW = S::TW, RPB = S::RPB;
-  if constexpr (NT > 0 && !LAST) {
-    uint32_t wa[2 * CA], wb[2 * CB];
-    tmem_ld_words<2 * CA>(tbase, wa);
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-      const double r = rr[R + t];
-      tmem_wait_ld();
-      tmem_ld_words<2 * CB>(tbase + (uint32_t)(t * TW + 2 * CA), wb);
-#pragma unroll
-      for (int c = 0; c < CA; c++) s[c] = fma(r, estep3_w2d(wa[2 * c], wa[2 * c + 1]), s[c]);
-      tmem_wait_ld();
-      if (t + 1 < NT) tmem_ld_words<2 * CA>(tbase + (uint32_t)((t + 1) * TW), wa);
-#pragma unroll
-      for (int c = 0; c < CB; c++) s[CA + c] = fma(r, estep3_w2d(wb[2 * c], wb[2 * c + 1]), s[CA + c]);
-    }
-  } else if constexpr (NT > 0) {
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-      uint32_t w32[TW];
-      tmem_ld_words<TW>(tbase + (uint32_t)t * TW, w32);
-      tmem_wait_ld();
-      double ev[KPL];
-#pragma unroll
-      for (int c = 0; c < KPL; c++) ev[c] = estep3_w2d(w32[2 * c], w32[2 * c + 1]);
-#pragma unroll
-      for (int c = 0; c < KPL; c++) s[c] = fma(rr[R + t], ev[c], s[c]);
-      if (a.learning && rr[R + t] > 0.0)
-        estep3_scatter<L, KPL>(a.stats + (size_t)(__ldg(a.term_id + zrow0 + (R + t) * RPB + g) - 1) * a.K,
-                               theta2, rr[R + t], ev, j, a.K);
-    }
-  }
-}
-template <int L, int KPL, int R, int NM, bool LAST>
-__device__ __forceinline__ void estep3_sacc_smem(const EstepArgs &a, const double2 *tile2,
-                                                 const double (&rr)[Estep3Shape<L, KPL, R>::NBMAX],
-                                                 double (&s)[KPL], const double2 *theta2,
-                                                 const int64_t zrow0, const int g, const int j) {
-  using S = Estep3Shape<L, KPL, R>;
-  constexpr int HALF = S::HALF, T = S::T, RPB = S::RPB;
-#pragma unroll
-  for (int m = 0; m < NM; m++) {
-    const double2 *src = tile2 + (size_t)m * HALF * 32;
-    const double r = rr[R + T + m];
-    double ev[KPL];
-#pragma unroll
-    for (int i = 0; i < HALF; i++) {
-      const double2 v = src[(size_t)i * 32];
-      ev[2 * i] = v.x;
-      ev[2 * i + 1] = v.y;
-    }
-#pragma unroll
-    for (int c = 0; c < KPL; c++) s[c] = fma(r, ev[c], s[c]);
-    if (LAST && a.learning && r > 0.0)
-      estep3_scatter<L, KPL>(a.stats + (size_t)(__ldg(a.term_id + zrow0 + (R + T + m) * RPB + g) - 1) * a.K,
-                             theta2, r, ev, j, a.K);
-  }
-}
-
-#define MRLDA_E3_DISPATCH(n_, CALL)            \
-  switch (n_) {                                \
-    case 1: { CALL(1); } break;                \
-    case 2: { CALL(2); } break;                \
-    case 3: { CALL(3); } break;                \
-    case 4: { CALL(4); } break;                \
-    default: break;                            \
-  }
-
-// One sweep over the batches of this warp.  e: register batches; tbase: this warp's TMEM slots;
-// tile2: this warp's shared-memory batches (+ lane); theta2: the group's theta as double2 pairs;
-// cnt_w: n_w of this warp's batch slots (0 for padding rows); zrow0: CSR offset of this warp's
-// first row; ntm / nsm: TMEM / shared-memory batches in use.
-template <int L, int KPL, int R, bool LAST>
-__device__ __forceinline__ void estep3_sweep(const EstepArgs &a, const double (&e)[R][KPL],
-                                             const uint32_t tbase, const double2 *tile2,
-                                             const double2 *theta2, const double *cnt_w,
-                                             double (&s)[KPL], double &lik, unsigned &badbits,
-                                             const int ntm, const int nsm, const int64_t zrow0,
-                                             const int g, const int j) {
-  using S = Estep3Shape<L, KPL, R>;
-  constexpr int RPB = S::RPB, HALF = S::HALF, T = S::T, NB = S::NBMAX;
-  double pr[NB];  // partial dot products -> norms
-  double rr[NB];  // r_w = n_w / norm_w
-#pragma unroll
-  for (int bi = 0; bi < NB; bi++) {  // slots that are not in use
-    pr[bi] = 1.0;
-    rr[bi] = 0.0;
-  }
+// One of the sweeps 1..I-1 over the batches of this warp: NTM TMEM and NSM shared-memory batches
+// in use (compile time), so the whole sweep is straight-line code.  Returns S in s, the underflow
+// flags in badbits.
+template <int L, int KPL, int R, int NW, int NTM, int NSM>
+__device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW> &w,
+                                                  const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
+                                                  double (&s)[KPL], unsigned &badbits) {
+  using S = Estep3Shape<L, KPL, R, NW>;
+  constexpr int RPB = S::RPB, HALF = S::HALF, T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
+  constexpr int NA = R + NTM + NSM;  // batches in use; batch i < R + NTM sits in slot i, the others in slot i - NTM + T
+  static_assert(NA > 0, "a warp that takes part in a document holds at least one batch");
+  double pr[NA];  // partial dot products -> norms
+  double rr[NA];  // r_w = n_w / norm_w
+  const int g = w.g, j = w.j;
+  uint32_t wa[2 * CA], wb[2 * CB];
   // ---- pass A: theta in registers; partial dot products of every batch ----
   {
     double th[KPL];
 #pragma unroll
     for (int i = 0; i < HALF; i++) {
-      const double2 v = theta2[j + L * i];
+      const double2 v = w.theta2[j + L * i];
       th[2 * i] = v.x;
       th[2 * i + 1] = v.y;
     }
-    {
-      double acc[R][4];
+    if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // in flight behind the register batches
+    if constexpr (R > 0) {
+      double acc[S::RA][4];
 #pragma unroll
       for (int q = 0; q < R; q++) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
 #pragma unroll
@@ -361,112 +208,326 @@ __device__ __forceinline__ void estep3_sweep(const EstepArgs &a, const double (&
 #pragma unroll
       for (int q = 0; q < R; q++) pr[q] = (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
     }
-#define MRLDA_E3_CALL(N) estep3_dots_tmem<L, KPL, R, N>(th, tbase, pr)
-    MRLDA_E3_DISPATCH(ntm, MRLDA_E3_CALL)
-#undef MRLDA_E3_CALL
-#define MRLDA_E3_CALL(N) estep3_dots_smem<L, KPL, R, N>(th, tile2, pr)
-    MRLDA_E3_DISPATCH(nsm, MRLDA_E3_CALL)
-#undef MRLDA_E3_CALL
+#pragma unroll
+    for (int t = 0; t < NTM; t++) {
+      tmem_wait_ld();
+      tmem_ld_words<2 * CB>(w.tbase + (uint32_t)(t * TW + 2 * CA), wb);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int c = 0; c < CA; c += 4) {
+        a0 = fma(th[c], estep3_w2d(wa[2 * c], wa[2 * c + 1]), a0);
+        a1 = fma(th[c + 1], estep3_w2d(wa[2 * c + 2], wa[2 * c + 3]), a1);
+        a2 = fma(th[c + 2], estep3_w2d(wa[2 * c + 4], wa[2 * c + 5]), a2);
+        a3 = fma(th[c + 3], estep3_w2d(wa[2 * c + 6], wa[2 * c + 7]), a3);
+      }
+      tmem_wait_ld();
+      if (t + 1 < NTM) tmem_ld_words<2 * CA>(w.tbase + (uint32_t)((t + 1) * TW), wa);
+#pragma unroll
+      for (int c = 0; c < CB; c += 2) {
+        if (c & 2) {
+          a2 = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), a2);
+          a3 = fma(th[CA + c + 1], estep3_w2d(wb[2 * c + 2], wb[2 * c + 3]), a3);
+        } else {
+          a0 = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), a0);
+          a1 = fma(th[CA + c + 1], estep3_w2d(wb[2 * c + 2], wb[2 * c + 3]), a1);
+        }
+      }
+      pr[R + t] = (a0 + a1) + (a2 + a3);
+    }
+#pragma unroll
+    for (int m = 0; m < NSM; m++) {
+      const double2 *src = w.tile2 + (size_t)m * HALF * 32;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+      for (int i = 0; i < HALF; i++) {
+        const double2 v = src[(size_t)i * 32];
+        if (i & 1) {
+          a2 = fma(th[2 * i], v.x, a2);
+          a3 = fma(th[2 * i + 1], v.y, a3);
+        } else {
+          a0 = fma(th[2 * i], v.x, a0);
+          a1 = fma(th[2 * i + 1], v.y, a1);
+        }
+      }
+      pr[R + NTM + m] = (a0 + a1) + (a2 + a3);
+    }
   }
-  // ---- norms (L-lane butterflies), r = n_w / norm_w ----
+  // ---- norms (L-lane butterflies), r = n_w / norm_w: every step runs over all batches ----
+  if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // pass B's first load, behind the chains
+#pragma unroll
+  for (int o = 1; o < L; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < NA; i++) pr[i] += __shfl_xor_sync(0xffffffffu, pr[i], o);
+  }
   int minhi = 0x7fffffff;
-  if (nsm > 0)
-    estep3_norms_to_r<L, KPL, R, NB>(pr, rr, cnt_w, g, minhi);
-  else if (ntm > 2)
-    estep3_norms_to_r<L, KPL, R, R + T>(pr, rr, cnt_w, g, minhi);
-  else
-    estep3_norms_to_r<L, KPL, R, R + 2>(pr, rr, cnt_w, g, minhi);
+  {
+    double y[NA], t1[NA];
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(pr[i]));
+      minhi = min(minhi, __double2hiint(pr[i]));
+    }
+#pragma unroll
+    for (int i = 0; i < NA; i++) t1[i] = fma(-pr[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NA; i++) y[i] = fma(y[i], t1[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < NA; i++) t1[i] = fma(-pr[i], y[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NA; i++) y[i] = fma(y[i], t1[i], y[i]);
+#pragma unroll
+    for (int i = 0; i < NA; i++) rr[i] = w.cnt_w[(i < R + NTM ? i : i - NTM + T) * RPB + g] * y[i];
+  }
   badbits = 0;
   if (__any_sync(0xffffffffu, minhi < __double2hiint(MRLDA_NORM_TINY))) {
     // some norm underflowed (rare): those rows contribute through the exact log-space redo
 #pragma unroll
-    for (int bi = 0; bi < NB; bi++) {
-      if (!(pr[bi] >= MRLDA_NORM_TINY)) {
-        if (cnt_w[bi * RPB + g] > 0.0) badbits |= 1u << bi;
-        rr[bi] = 0.0;
+    for (int i = 0; i < NA; i++) {
+      if (!(pr[i] >= MRLDA_NORM_TINY)) {
+        const int slot = i < R + NTM ? i : i - NTM + T;
+        if (w.cnt_w[slot * RPB + g] > 0.0) badbits |= 1u << slot;
+        rr[i] = 0.0;
       }
-    }
-  }
-  if (LAST && j == 0) {  // likelihoodPhi, first part (DocumentMapper.java:421 summed over topics)
-#pragma unroll
-    for (int bi = 0; bi < NB; bi++) {
-      if (rr[bi] > 0.0)
-        lik = fma(cnt_w[bi * RPB + g], log(pr[bi]) + __ldg(a.rowmax + __ldg(a.term_id + zrow0 + bi * RPB + g) - 1), lik);
     }
   }
   // ---- pass B: S_c += r_w E_wc ----
 #pragma unroll
   for (int c = 0; c < KPL; c++) s[c] = 0.0;
 #pragma unroll
-  for (int c = 0; c < KPL; c++) {
+  for (int q = 0; q < R; q++) {
 #pragma unroll
-    for (int q = 0; q < R; q++) s[c] = fma(rr[q], e[q][c], s[c]);
+    for (int c = 0; c < KPL; c++) s[c] = fma(rr[q], e[q][c], s[c]);
   }
-  if (LAST && a.learning) {
 #pragma unroll
-    for (int q = 0; q < R; q++)
-      if (rr[q] > 0.0)
-        estep3_scatter<L, KPL>(a.stats + (size_t)(__ldg(a.term_id + zrow0 + q * RPB + g) - 1) * a.K, theta2,
-                               rr[q], e[q], j, a.K);
+  for (int t = 0; t < NTM; t++) {
+    const double r = rr[R + t];
+    tmem_wait_ld();
+    tmem_ld_words<2 * CB>(w.tbase + (uint32_t)(t * TW + 2 * CA), wb);
+#pragma unroll
+    for (int c = 0; c < CA; c++) s[c] = fma(r, estep3_w2d(wa[2 * c], wa[2 * c + 1]), s[c]);
+    tmem_wait_ld();
+    if (t + 1 < NTM) tmem_ld_words<2 * CA>(w.tbase + (uint32_t)((t + 1) * TW), wa);
+#pragma unroll
+    for (int c = 0; c < CB; c++) s[CA + c] = fma(r, estep3_w2d(wb[2 * c], wb[2 * c + 1]), s[CA + c]);
   }
-#define MRLDA_E3_CALL(N) estep3_sacc_tmem<L, KPL, R, N, LAST>(a, tbase, rr, s, theta2, zrow0, g, j)
-  MRLDA_E3_DISPATCH(ntm, MRLDA_E3_CALL)
-#undef MRLDA_E3_CALL
-#define MRLDA_E3_CALL(N) estep3_sacc_smem<L, KPL, R, N, LAST>(a, tile2, rr, s, theta2, zrow0, g, j)
-  MRLDA_E3_DISPATCH(nsm, MRLDA_E3_CALL)
-#undef MRLDA_E3_CALL
+#pragma unroll
+  for (int m = 0; m < NSM; m++) {
+    const double2 *src = w.tile2 + (size_t)m * HALF * 32;
+    const double r = rr[R + NTM + m];
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+      const double2 v = src[(size_t)i * 32];
+      s[2 * i] = fma(r, v.x, s[2 * i]);
+      s[2 * i + 1] = fma(r, v.y, s[2 * i + 1]);
+    }
+  }
 }
 
-// sum of the RPB * G partial sums of column col that the group's warps published
+// The last sweep (generic over the batch count): one fused pass per batch with the likelihood terms
+// (DocumentMapper.java:421) and the statistics scatter (:315-329).
 template <int L, int KPL>
-__device__ __forceinline__ double estep3_colsum(const double *spart, const int w0, const int G, const int col) {
+__device__ __forceinline__ void estep3_last_batch(const EstepArgs &a, const double2 *theta2, const double *cnt_w,
+                                                  const double (&ev)[KPL], const int slot, const int64_t zrow0,
+                                                  const int g, const int j, double (&s)[KPL], double &lik,
+                                                  unsigned &badbits) {
+  constexpr int RPB = 32 / L, HALF = KPL / 2;
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+  for (int i = 0; i < HALF; i++) {
+    const double2 tv = theta2[j + L * i];
+    a0 = fma(tv.x, ev[2 * i], a0);
+    a1 = fma(tv.y, ev[2 * i + 1], a1);
+  }
+  double p = a0 + a1;
+#pragma unroll
+  for (int o = 1; o < L; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  const double cn = cnt_w[slot * RPB + g];
+  const bool ok = p >= MRLDA_NORM_TINY;
+  if (cn > 0.0 && !ok) badbits |= 1u << slot;
+  const double r = (cn > 0.0 && ok) ? cn * rcp_fast(ok ? p : 1.0) : 0.0;
+#pragma unroll
+  for (int c = 0; c < KPL; c++) s[c] = fma(r, ev[c], s[c]);
+  if (r > 0.0) {
+    const int term = __ldg(a.term_id + zrow0 + slot * RPB + g);
+    if (j == 0) lik = fma(cn, log(p) + __ldg(a.rowmax + term - 1), lik);
+    if (a.learning) estep3_scatter<L, KPL>(a.stats + (size_t)(term - 1) * a.K, theta2, r, ev, j, a.K);
+  }
+}
+template <int L, int KPL, int R, int NW>
+__device__ __forceinline__ void estep3_sweep_last(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
+                                                  const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
+                                                  double (&s)[KPL], double &lik, unsigned &badbits,
+                                                  const int nb, const int64_t zrow0) {
+  using S = Estep3Shape<L, KPL, R, NW>;
+  constexpr int HALF = S::HALF, T = S::T, TW = S::TW;
+  badbits = 0;
+#pragma unroll
+  for (int c = 0; c < KPL; c++) s[c] = 0.0;
+#pragma unroll
+  for (int q = 0; q < R; q++)
+    estep3_last_batch<L, KPL>(a, w.theta2, w.cnt_w, e[q], q, zrow0, w.g, w.j, s, lik, badbits);
+#pragma unroll 1
+  for (int t = 0; R + t < nb && t < T; t++) {
+    uint32_t w32[TW];
+    tmem_ld_words<TW>(w.tbase + (uint32_t)t * TW, w32);
+    tmem_wait_ld();
+    double ev[KPL];
+#pragma unroll
+    for (int c = 0; c < KPL; c++) ev[c] = estep3_w2d(w32[2 * c], w32[2 * c + 1]);
+    estep3_last_batch<L, KPL>(a, w.theta2, w.cnt_w, ev, R + t, zrow0, w.g, w.j, s, lik, badbits);
+  }
+#pragma unroll 1
+  for (int m = 0; R + T + m < nb; m++) {
+    const double2 *src = w.tile2 + (size_t)m * HALF * 32;
+    double ev[KPL];
+#pragma unroll
+    for (int i = 0; i < HALF; i++) {
+      const double2 v = src[(size_t)i * 32];
+      ev[2 * i] = v.x;
+      ev[2 * i + 1] = v.y;
+    }
+    estep3_last_batch<L, KPL>(a, w.theta2, w.cnt_w, ev, R + T + m, zrow0, w.g, w.j, s, lik, badbits);
+  }
+}
+
+// sum of the RPB * nw partial sums of column col that warps [w0, w0 + nw) published
+template <int L, int KPL>
+__device__ __forceinline__ double estep3_colsum(const double *spart, const int w0, const int nw, const int col) {
   constexpr int RPB = 32 / L, HALF = KPL / 2;
   const int i = (col >> 1) / L, jj = (col >> 1) % L;
   const double *p = spart + ((size_t)(w0 * HALF + i) * 32 + jj) * 2 + (col & 1);
-  double s0 = 0.0, s1 = 0.0;
-  for (int w2 = 0; w2 < G; w2++) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 2
+  for (int w2 = 0; w2 < nw; w2++) {
 #pragma unroll
     for (int gg = 0; gg < RPB; gg++) {
       const double v = p[(size_t)w2 * HALF * 64 + gg * L * 2];
-      if (gg & 1) s1 += v;
-      else s0 += v;
+      if ((gg & 3) == 0) s0 += v;
+      else if ((gg & 3) == 1) s1 += v;
+      else if ((gg & 3) == 2) s2 += v;
+      else s3 += v;
     }
   }
-  return s0 + s1;
+  return (s0 + s1) + (s2 + s3);
 }
 
-template <int L, int KPL, int R>
-__global__ void __launch_bounds__(256, 1) estep3_kernel(const EstepArgs a) {
-  using S = Estep3Shape<L, KPL, R>;
+// Per-group state in shared memory and the launch geometry of the group this thread belongs to.
+struct Estep3Group {
+  double *spart, *theta_g, *gam_g, *gextra_g, *alpha_s;
+  int w0, G, gt, GT, bar_id, K;
+};
+
+// column owners after a sweep that is not the last: gamma_c = alpha_c + theta_c S_c
+// (DocumentMapper.java:232-234) and the next theta_c = exp(digamma(gamma_c)), two columns at a time
+template <int L, int KPL>
+__device__ __forceinline__ void estep3_update_gamma(const Estep3Group &q) {
+  for (int col = q.gt; col < q.K; col += 2 * q.GT) {
+    const int col2 = col + q.GT;
+    const bool two = col2 < q.K;
+    const double s0 = estep3_colsum<L, KPL>(q.spart, q.w0, q.G, col);
+    const double s1 = estep3_colsum<L, KPL>(q.spart, q.w0, q.G, two ? col2 : col);
+    const double g0 = fma(q.theta_g[col], s0, q.alpha_s[col]) + q.gextra_g[col];
+    const double g1 = two ? fma(q.theta_g[col2], s1, q.alpha_s[col2]) + q.gextra_g[col2] : 1.0;
+    q.gextra_g[col] = 0.0;
+    q.gam_g[col] = g0;
+    const double t0 = exp_digamma(g0);
+    const double t1 = exp_digamma(g1);
+    q.theta_g[col] = t0;
+    if (two) {
+      q.gextra_g[col2] = 0.0;
+      q.gam_g[col2] = g1;
+      q.theta_g[col2] = t1;
+    }
+  }
+}
+
+// sweeps 1..I-1 of one document for a warp that holds NTM TMEM and NSM shared-memory batches
+template <int L, int KPL, int R, int NW, int NTM, int NSM>
+__device__ __forceinline__ void estep3_run_sweeps(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
+                                                  const Estep3Group &q,
+                                                  const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
+                                                  double2 *spart_w, const int nb, const int64_t zrow0,
+                                                  const int lane) {
+  constexpr int HALF = KPL / 2;
+  for (int sweep = 0; sweep < a.sweeps - 1; sweep++) {
+    double s[KPL];
+    unsigned badbits;
+    estep3_sweep_fast<L, KPL, R, NW, NTM, NSM>(w, e, s, badbits);
+    if (__any_sync(0xffffffffu, badbits != 0))
+      (void)estep3_slow_rows<L>(a.term_id + zrow0, a.count + zrow0, a.logbeta, nullptr, a.slow_rows, q.gam_g,
+                                q.gextra_g, q.K, nb, badbits, lane, false);
+    // S partials of every lane as they are; the column owners sum them
+#pragma unroll
+    for (int i = 0; i < HALF; i++) spart_w[(size_t)i * 32] = make_double2(s[2 * i], s[2 * i + 1]);
+    estep3_group_sync(q.bar_id, q.GT);  // B1: S partials (and slow-path contributions) complete
+    estep3_update_gamma<L, KPL>(q);
+    estep3_group_sync(q.bar_id, q.GT);  // B2: theta published
+  }
+}
+
+// picks the specialisation for this warp's batch count (once per document)
+template <int L, int KPL, int R, int NW, int NB_>
+__device__ __forceinline__ void estep3_dispatch(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
+                                                const Estep3Group &q,
+                                                const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
+                                                double2 *spart_w, const int nb, const int64_t zrow0,
+                                                const int lane) {
+  using S = Estep3Shape<L, KPL, R, NW>;
+  constexpr int NTM = NB_ > R ? (NB_ - R < S::T ? NB_ - R : S::T) : 0;
+  constexpr int NSM = NB_ > R + S::T ? NB_ - R - S::T : 0;
+  if constexpr (NB_ >= S::NBMAX) {
+    estep3_run_sweeps<L, KPL, R, NW, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
+  } else {
+    if (nb <= NB_)
+      estep3_run_sweeps<L, KPL, R, NW, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
+    else
+      estep3_dispatch<L, KPL, R, NW, NB_ + 1>(a, w, q, e, spart_w, nb, zrow0, lane);
+  }
+}
+
+template <int L, int KPL, int R, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
+  using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int RPB = S::RPB, KS = S::KS, HALF = S::HALF, TW = S::TW, T = S::T, NBMAX = S::NBMAX;
+  constexpr int THREADS = S::THREADS;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int g = lane / L, j = lane % L;
   const int K = a.K;
   const int G = a.group_warps, M = a.smem_batches;
-  const int grp = warp / G, gw = warp % G, gt = gw * 32 + lane, GT = 32 * G;
-  const int bar_id = 1 + grp;
-  const Estep3Smem<L, KPL, R> lay(M, G);
+  const int grp = warp / G, gw = warp % G;
+  const Estep3Smem<L, KPL, R, NW> lay(M, G);
 
+  Estep3Warp<L, KPL, R, NW> w;
+  w.g = lane / L;
+  w.j = lane % L;
   double2 *tile2 = reinterpret_cast<double2 *>(smem + lay.tile) + (size_t)warp * M * HALF * 32 + lane;
-  double *spart = smem + lay.spart;
-  double2 *spart_w = reinterpret_cast<double2 *>(spart) + (size_t)warp * HALF * 32 + lane;
-  double *theta_g = smem + lay.theta + (size_t)grp * KS;
-  double *gam_g = smem + lay.gam + (size_t)grp * KS;
-  double *gextra_g = smem + lay.gextra + (size_t)grp * KS;
-  double *alpha_s = smem + lay.alpha;
-  double *ssacc_s = smem + lay.ssacc;
+  w.tile2 = tile2;
   double *cnt_w = smem + lay.cnt + (size_t)warp * (NBMAX * RPB);
+  w.cnt_w = cnt_w;
+  Estep3Group q;
+  q.spart = smem + lay.spart;
+  q.theta_g = smem + lay.theta + (size_t)grp * KS;
+  q.gam_g = smem + lay.gam + (size_t)grp * KS;
+  q.gextra_g = smem + lay.gextra + (size_t)grp * KS;
+  q.alpha_s = smem + lay.alpha;
+  q.w0 = grp * G;
+  q.G = G;
+  q.gt = gw * 32 + lane;
+  q.GT = 32 * G;
+  q.bar_id = 1 + grp;
+  q.K = K;
+  w.theta2 = reinterpret_cast<const double2 *>(q.theta_g);
+  double2 *spart_w = reinterpret_cast<double2 *>(q.spart) + (size_t)warp * HALF * 32 + lane;
+  double *ssacc_s = smem + lay.ssacc;
   double *red_s = smem + lay.red;  // [warp][4]
   int *meta_s = reinterpret_cast<int *>(smem + lay.meta);  // [0] TMEM base, [1 + grp] document
-  const double2 *theta2 = reinterpret_cast<const double2 *>(theta_g);
 
-  for (int k = tid; k < KS; k += 256) {
-    alpha_s[k] = k < K ? a.alpha[k] : 1.0;
+  for (int k = tid; k < KS; k += THREADS) {
+    q.alpha_s[k] = k < K ? a.alpha[k] : 1.0;
     ssacc_s[k] = 0.0;
   }
-  for (int k = tid; k < (8 / G) * KS; k += 256) {
+  for (int k = tid; k < (NW / G) * KS; k += THREADS) {
     smem[lay.theta + k] = 0.0;
     smem[lay.gam + k] = 1.0;
     smem[lay.gextra + k] = 0.0;
@@ -476,13 +537,13 @@ __global__ void __launch_bounds__(256, 1) estep3_kernel(const EstepArgs a) {
   tmem_fence_before_sync();
   __syncthreads();
   tmem_fence_after_sync();
-  const uint32_t tbase = (uint32_t)meta_s[0] + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 256u;
+  w.tbase = (uint32_t)meta_s[0] + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * (uint32_t)S::TWORDS;
   const double lik_alpha = *a.lik_alpha;
 
   for (;;) {
-    estep3_group_sync(bar_id, GT);  // everybody is done with the previous document's shared state
-    if (gt == 0) meta_s[1 + grp] = a.doc_begin + atomicAdd(a.work_counter, 1);
-    estep3_group_sync(bar_id, GT);
+    estep3_group_sync(q.bar_id, q.GT);  // everybody is done with the previous document's shared state
+    if (q.gt == 0) meta_s[1 + grp] = a.doc_begin + atomicAdd(a.work_counter, 1);
+    estep3_group_sync(q.bar_id, q.GT);
     const int qi = meta_s[1 + grp];
     if (qi >= a.doc_end) break;
     const int d = a.doc_order[qi];
@@ -495,30 +556,29 @@ __global__ void __launch_bounds__(256, 1) estep3_kernel(const EstepArgs a) {
     const int nb = nb_lo + (gw < nb_rem ? 1 : 0);
     const int bstart = gw * nb_lo + (gw < nb_rem ? gw : nb_rem);
     const int64_t zrow0 = b + (int64_t)bstart * RPB;
-    const int ntm = nb > R ? (nb - R < T ? nb - R : T) : 0;
-    const int nsm = nb > R + T ? nb - R - T : 0;
 
     // ---- load my batches: complete E rows, L lanes per row (compulsory traffic).  Padding rows
     // are a copy of the document's last row with n_w = 0. ----
     for (int x = lane; x < NBMAX * RPB; x += 32) cnt_w[x] = 0.0;
     __syncwarp();
-    double e[R][KPL];
+    double e[S::RA][KPL];
 #pragma unroll
     for (int bi = 0; bi < NBMAX; bi++) {
-      if (bi < R || bi < nb) {  // warp-uniform
-        const int row = (bstart + bi) * RPB + g;
+      if (bi < R || bi < nb || bi == 0) {  // warp-uniform (slot 0 always holds a row: a warp without
+                                           // batches walks one padding batch)
+        const int row = (bstart + bi) * RPB + w.g;
         const bool valid = bi < nb && row < n;
         const int rowc = valid ? row : n - 1;
         double v[KPL];
         const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + rowc) - 1) * a.e_stride) + j;
+            a.E + (size_t)(__ldg(a.term_id + b + rowc) - 1) * a.e_stride) + w.j;
 #pragma unroll
         for (int i = 0; i < HALF; i++) {
           const double2 t2 = __ldg(src + L * i);
           v[2 * i] = t2.x;
           v[2 * i + 1] = t2.y;
         }
-        if (valid && j == 0) cnt_w[bi * RPB + g] = (double)__ldg(a.count + b + row);
+        if (valid && w.j == 0) cnt_w[bi * RPB + w.g] = (double)__ldg(a.count + b + row);
         if (bi < R) {
 #pragma unroll
           for (int c = 0; c < KPL; c++) e[bi < R ? bi : 0][c] = v[c];
@@ -529,7 +589,7 @@ __global__ void __launch_bounds__(256, 1) estep3_kernel(const EstepArgs a) {
             w32[2 * c] = (uint32_t)__double2loint(v[c]);
             w32[2 * c + 1] = (uint32_t)__double2hiint(v[c]);
           }
-          tmem_st_words<TW>(tbase + (uint32_t)(bi - R) * TW, w32);
+          tmem_st_words<TW>(w.tbase + (uint32_t)(bi - R) * TW, w32);
         } else {
           double2 *dst = tile2 + (size_t)(bi - R - T) * HALF * 32;
 #pragma unroll
@@ -541,100 +601,74 @@ __global__ void __launch_bounds__(256, 1) estep3_kernel(const EstepArgs a) {
     // gamma start (DocumentMapper.java:184-193) and the first theta, by the column owners
     {
       const double share = (double)((float)a.doc_tokens[d] / (float)K);
-      for (int col = gt; col < K; col += GT) {
-        const double gam = a.use_stored_gamma ? a.gamma[(size_t)d * K + col] : alpha_s[col] + share;
-        gam_g[col] = gam;
-        theta_g[col] = exp_digamma(gam);
+      for (int col = q.gt; col < K; col += q.GT) {
+        const double gam = a.use_stored_gamma ? a.gamma[(size_t)d * K + col] : q.alpha_s[col] + share;
+        q.gam_g[col] = gam;
+        q.theta_g[col] = exp_digamma(gam);
       }
     }
-    estep3_group_sync(bar_id, GT);
+    estep3_group_sync(q.bar_id, q.GT);
 
-    double lik = 0.0;
-    for (int sweep = 0; sweep < a.sweeps; sweep++) {
-      const bool last = (sweep == a.sweeps - 1);
+    // a warp without rows (short document, more warps than batches) still takes part in the barriers
+    // ---- sweeps 1..I-1: loop body specialised on this warp's batch count ----
+    estep3_dispatch<L, KPL, R, NW, (R > 1 ? R : 1)>(a, w, q, e, spart_w, nb, zrow0, lane);
+
+    // ---- last sweep, document epilogue (DocumentMapper.java:244-259,342-346) ----
+    {
       double s[KPL];
+      double lik = 0.0;
       unsigned badbits;
-      if (!last)
-        estep3_sweep<L, KPL, R, false>(a, e, tbase, tile2, theta2, cnt_w, s, lik, badbits, ntm, nsm, zrow0, g, j);
-      else
-        estep3_sweep<L, KPL, R, true>(a, e, tbase, tile2, theta2, cnt_w, s, lik, badbits, ntm, nsm, zrow0, g, j);
+      estep3_sweep_last<L, KPL, R, NW>(a, w, e, s, lik, badbits, nb, zrow0);
       if (__any_sync(0xffffffffu, badbits != 0))
         lik += estep3_slow_rows<L>(a.term_id + zrow0, a.count + zrow0, a.logbeta, a.learning ? a.stats : nullptr,
-                                   a.slow_rows, gam_g, gextra_g, K, nb, badbits, lane, last);
-      // S partials of every lane as they are; the column owners sum them
+                                   a.slow_rows, q.gam_g, q.gextra_g, K, nb, badbits, lane, true);
 #pragma unroll
       for (int i = 0; i < HALF; i++) spart_w[(size_t)i * 32] = make_double2(s[2 * i], s[2 * i + 1]);
-      if (last) {
-        lik = warp_sum(lik);
-        if (lane == 0) red_s[warp * 4 + 3] = lik;
+      lik = warp_sum(lik);
+      if (lane == 0) red_s[warp * 4 + 3] = lik;
+      estep3_group_sync(q.bar_id, q.GT);
+      double sg = 0.0, lg = 0.0, lk = 0.0;
+      for (int col = q.gt; col < K; col += q.GT) {
+        const double sk = estep3_colsum<L, KPL>(q.spart, q.w0, G, col);
+        const double add = q.theta_g[col] * sk;
+        const double g_old = q.gam_g[col];
+        const double g_new = q.alpha_s[col] + add + q.gextra_g[col];
+        q.gextra_g[col] = 0.0;
+        if (add != 0.0) lk -= digamma_fast(g_old) * add;
+        q.gam_g[col] = g_new;
+        sg += g_new;
+        lg += lgamma(g_new);
+        a.gamma[(size_t)d * K + col] = g_new;
       }
-      estep3_group_sync(bar_id, GT);  // B1: S partials (and slow-path contributions) complete
-      if (!last) {
-        // column owners: gamma_c = alpha_c + theta_c S_c (DocumentMapper.java:232-234), next theta
-        for (int col = gt; col < K; col += 2 * GT) {
-          const int col2 = col + GT;
-          const bool two = col2 < K;
-          const double s0 = estep3_colsum<L, KPL>(spart, grp * G, G, col);
-          const double s1 = estep3_colsum<L, KPL>(spart, grp * G, G, two ? col2 : col);
-          const double g0 = fma(theta_g[col], s0, alpha_s[col]) + gextra_g[col];
-          const double g1 = two ? fma(theta_g[col2], s1, alpha_s[col2]) + gextra_g[col2] : 1.0;
-          gextra_g[col] = 0.0;
-          gam_g[col] = g0;
-          const double t0 = exp_digamma(g0);
-          const double t1 = exp_digamma(g1);
-          theta_g[col] = t0;
-          if (two) {
-            gextra_g[col2] = 0.0;
-            gam_g[col2] = g1;
-            theta_g[col2] = t1;
-          }
-        }
-        estep3_group_sync(bar_id, GT);  // B2: theta published
-      } else {
-        // ---- document epilogue (DocumentMapper.java:244-259,342-346) ----
-        double sg = 0.0, lg = 0.0, lk = 0.0;
-        for (int col = gt; col < K; col += GT) {
-          const double sk = estep3_colsum<L, KPL>(spart, grp * G, G, col);
-          const double add = theta_g[col] * sk;
-          const double g_old = gam_g[col];
-          const double g_new = alpha_s[col] + add + gextra_g[col];
-          gextra_g[col] = 0.0;
-          if (add != 0.0) lk -= digamma_fast(g_old) * add;
-          gam_g[col] = g_new;
-          sg += g_new;
-          lg += lgamma(g_new);
-          a.gamma[(size_t)d * K + col] = g_new;
-        }
-        sg = warp_sum(sg);
-        lg = warp_sum(lg);
-        lk = warp_sum(lk);
-        if (lane == 0) {
-          red_s[warp * 4 + 0] = sg;
-          red_s[warp * 4 + 1] = lg;
-          red_s[warp * 4 + 2] = lk;
-        }
-        estep3_group_sync(bar_id, GT);
-        double tg = 0.0, tl = 0.0, tk = 0.0;
-        for (int w2 = 0; w2 < G; w2++) {
-          const double *rp = red_s + (grp * G + w2) * 4;
-          tg += rp[0];
-          tl += rp[1];
-          tk += rp[2] + rp[3];
-        }
-        const double dsg = digamma_literal(tg);
-        for (int col = gt; col < K; col += GT) atomicAdd(ssacc_s + col, digamma_literal(gam_g[col]) - dsg);
-        if (gt == 0) {
-          const double ll = lik_alpha + (tl - lgamma(tg)) + tk;
-          const long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
-          atomicAdd(a.ll_counter, (unsigned long long)c);
-        }
+      sg = warp_sum(sg);
+      lg = warp_sum(lg);
+      lk = warp_sum(lk);
+      if (lane == 0) {
+        red_s[warp * 4 + 0] = sg;
+        red_s[warp * 4 + 1] = lg;
+        red_s[warp * 4 + 2] = lk;
+      }
+      estep3_group_sync(q.bar_id, q.GT);
+      double tg = 0.0, tl = 0.0, tk = 0.0;
+      for (int w2 = 0; w2 < G; w2++) {
+        const double *rp = red_s + (q.w0 + w2) * 4;
+        tg += rp[0];
+        tl += rp[1];
+        tk += rp[2] + rp[3];
+      }
+      const double dsg = digamma_literal(tg);
+      for (int col = q.gt; col < K; col += q.GT) atomicAdd(ssacc_s + col, digamma_literal(q.gam_g[col]) - dsg);
+      if (q.gt == 0) {
+        const double ll = lik_alpha + (tl - lgamma(tg)) + tk;
+        const long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
+        atomicAdd(a.ll_counter, (unsigned long long)c);
       }
     }
   }
   // DocumentMapper.close (DocumentMapper.java:354-361)
   tmem_fence_before_sync();
   __syncthreads();
-  for (int k = tid; k < K; k += 256) {
+  for (int k = tid; k < K; k += THREADS) {
     const double v = ssacc_s[k];
     if (v != 0.0) atomicAdd(a.alpha_ss + k, v);
   }
@@ -642,36 +676,39 @@ __global__ void __launch_bounds__(256, 1) estep3_kernel(const EstepArgs a) {
 }
 
 struct Estep3Variant {
-  int L, KPL, R, T;
+  int L, KPL, R, T, NW, MMAX;
   cudaError_t (*launch)(const EstepArgs &, int grid, int G, int M, size_t smem, cudaStream_t);
   size_t (*smem_bytes)(int M, int G);
   cudaError_t (*prepare)(size_t smem);
 };
 
-template <int L, int KPL, int R>
+template <int L, int KPL, int R, int NW>
 static size_t variant3_smem(int M, int G) {
-  return Estep3Smem<L, KPL, R>(M, G).total;
+  return Estep3Smem<L, KPL, R, NW>(M, G).total;
 }
-template <int L, int KPL, int R>
+template <int L, int KPL, int R, int NW>
 static cudaError_t variant3_prepare(size_t smem) {
-  return cudaFuncSetAttribute(estep3_kernel<L, KPL, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return cudaFuncSetAttribute(estep3_kernel<L, KPL, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <int L, int KPL, int R>
+template <int L, int KPL, int R, int NW>
 static cudaError_t variant3_launch(const EstepArgs &args, int grid, int G, int M, size_t smem, cudaStream_t st) {
   EstepArgs a = args;
   a.group_warps = G;
   a.smem_batches = M;
-  estep3_kernel<L, KPL, R><<<grid, 256, smem, st>>>(a);
+  estep3_kernel<L, KPL, R, NW><<<grid, NW * 32, smem, st>>>(a);
   return cudaGetLastError();
 }
 
-#define MRLDA_VARIANT3(L_, KPL_, R_)                                                       \
-  {                                                                                        \
-    L_, KPL_, R_, Estep3Shape<L_, KPL_, R_>::T, variant3_launch<L_, KPL_, R_>,             \
-        variant3_smem<L_, KPL_, R_>, variant3_prepare<L_, KPL_, R_>                        \
+#define MRLDA_VARIANT3(L_, KPL_, R_, NW_)                                                          \
+  {                                                                                                \
+    L_, KPL_, R_, Estep3Shape<L_, KPL_, R_, NW_>::T, NW_, Estep3Shape<L_, KPL_, R_, NW_>::MMAX,     \
+        variant3_launch<L_, KPL_, R_, NW_>, variant3_smem<L_, KPL_, R_, NW_>,                      \
+        variant3_prepare<L_, KPL_, R_, NW_>                                                        \
   }
 
 extern const Estep3Variant g_estep3_variants_L8[];
 extern const int g_estep3_variants_L8_n;
+extern const Estep3Variant g_estep3_variants_L8b[];
+extern const int g_estep3_variants_L8b_n;
 
 }  // namespace mrlda

@@ -541,13 +541,15 @@ static const Estep2Variant *select_variant2(int K) {
 static const Estep3Variant *select_variant3(int K) {
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");
   if (fk && (atoi(fk) == 1 || atoi(fk) == 2)) return nullptr;
-  const Estep3Variant *tabs[] = {g_estep3_variants_L8};
-  const int ns[] = {g_estep3_variants_L8_n};
+  const char *fw = getenv("MRLDA_ESTEP3_NW");  // warps per CTA: 8 (default), 12 or 16 (profiling aid)
+  const int want_nw = fw ? atoi(fw) : 8;
+  const Estep3Variant *tabs[] = {g_estep3_variants_L8, g_estep3_variants_L8b};
+  const int ns[] = {g_estep3_variants_L8_n, g_estep3_variants_L8b_n};
   const Estep3Variant *best = nullptr;
   for (size_t t = 0; t < sizeof(ns) / sizeof(ns[0]); t++)
     for (int i = 0; i < ns[t]; i++) {
       const Estep3Variant *v = &tabs[t][i];
-      if (v->L * v->KPL < K) continue;
+      if (v->L * v->KPL < K || v->NW != want_nw) continue;
       if (!best || v->L * v->KPL < best->L * best->KPL) best = v;
     }
   return best;
@@ -1189,30 +1191,36 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   // (G warps per document, 8/G documents in flight per SM) takes the documents of at most
   // G * (R + T + M_G) * RPB rows that do not fit class G/2.  One launch per class, longest first.
   const Estep3Variant *v3 = (use2f || !use2) ? nullptr : ctx->variant3;
-  int cls_begin[5] = {0, 0, 0, 0, 0}, cls_M[4] = {0, 0, 0, 0};
-  size_t cls_smem[4] = {0, 0, 0, 0};
+  enum { MAXCLS = 6 };
+  int ncls = 0, cls_G[MAXCLS], cls_begin[MAXCLS + 1], cls_M[MAXCLS];
+  size_t cls_smem[MAXCLS];
   if (v3 && ctx->D > 0) {
     const size_t per = std::min((size_t)233472 - 1024, ctx->smem_optin) & ~(size_t)15;
     const int rpb = 32 / v3->L;
-    const char *fg = getenv("MRLDA_ESTEP3_GROUPS");  // bit mask of allowed group sizes (profiling aid)
-    const int gmask = fg ? atoi(fg) : 15;
+    const char *fg = getenv("MRLDA_ESTEP3_GROUPS");  // bit mask over the group sizes, largest first (profiling aid)
+    const int gmask = fg ? atoi(fg) : ~0;
+    // group sizes: the divisors of NW, largest first (named barriers 1..15: at most 15 groups)
+    for (int G = v3->NW, bit = 0; G >= 1 && ncls < MAXCLS; G--) {
+      if (v3->NW % G != 0 || v3->NW / G > 15) continue;
+      if (ncls == 0 || ((gmask >> bit) & 1)) cls_G[ncls++] = G;
+      bit++;
+    }
     bool ok3 = true;
-    cls_begin[4] = (int)ctx->D;
-    for (int ci = 3; ci >= 0; ci--) {  // ci: 0 -> G=8, 1 -> G=4, 2 -> G=2, 3 -> G=1
-      const int G = 8 >> ci;
-      int M = 4;
+    for (int ci = 0; ci < ncls; ci++) {
+      const int G = cls_G[ci];
+      int M = v3->MMAX;
       while (M > 0 && v3->smem_bytes(M, G) > per) M--;
       if (v3->smem_bytes(M, G) > per) ok3 = false;
       cls_M[ci] = M;
       cls_smem[ci] = v3->smem_bytes(M, G);
-      const bool enabled = ci == 0 || ((gmask >> (3 - ci)) & 1);
       const int capG = G * (v3->R + v3->T + M) * rpb;
       // first document (in descending nnz order) that fits class ci
-      cls_begin[ci] = !enabled ? cls_begin[ci + 1]
-                               : (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), capG,
-                                                        [](int cap, int32_t nn) { return cap >= nn; }) -
-                                       ctx->h_nnz_sorted.begin());
+      cls_begin[ci] = (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), capG,
+                                             [](int cap, int32_t nn) { return cap >= nn; }) -
+                            ctx->h_nnz_sorted.begin());
+      if (ci > 0) cls_begin[ci] = std::max(cls_begin[ci], cls_begin[ci - 1]);
     }
+    cls_begin[ncls] = (int)ctx->D;
     if (ok3) {
       n_long = cls_begin[0];
       grid2 = 0;
@@ -1242,15 +1250,15 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       ctx->launches++;
       if (fork) CK(cudaEventRecord(ctx->ev[7], ctx->stream2));
     }
-    for (int ci = 0; ci < 4; ci++) {
+    for (int ci = 0; ci < ncls; ci++) {
       const int nd = cls_begin[ci + 1] - cls_begin[ci];
       if (nd <= 0) continue;
-      const int G = 8 >> ci;
+      const int G = cls_G[ci], per_cta = v3->NW / G;
       a.doc_begin = cls_begin[ci];
       a.doc_end = cls_begin[ci + 1];
       a.work_counter = ctx->d_work + 4 + ci;
       CK(v3->prepare(cls_smem[ci]));
-      const int grid = (int)std::min<int64_t>(ctx->num_sms, ((int64_t)nd + (8 / G) - 1) / (8 / G));
+      const int grid = (int)std::min<int64_t>(ctx->num_sms, ((int64_t)nd + per_cta - 1) / per_cta);
       CK(v3->launch(a, grid, G, cls_M[ci], cls_smem[ci], st));
       ctx->launches++;
     }

