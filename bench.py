@@ -100,7 +100,7 @@ def algorithmic_flops(Z, D, K, sweeps=99):
 def cpu_reference_rate(c, logbeta, alpha, target_s=15.0):
     """Times the oracle's E-step (all host threads) on a bounded document sample."""
     from oracle import oracle as O
-    cores = O.num_threads()
+    cores = O.set_num_threads()  # every core this process may run on; OMP_NUM_THREADS is ignored
     D = c.n_docs
     pilot = min(D, 4 * max(cores, 8))
     sub = c.slice_docs(0, pilot)
@@ -143,32 +143,52 @@ def main():
     wl = {"workload": f"{args.workload}-shape synthetic corpus", "D": int(round(D0 * args.scale)),
           "V": V, "K": K, "sweeps": 99, "init": "alpha=1e-3, logbeta=log(2U1/V+U2) seed 7, cold gamma"}
 
+    seed = list(corpus.SHAPES).index(args.workload) + 1
+    heavy = corpus.SHAPES[args.workload][4]
+
+    def config_of(c, world_):
+        return dict(wl, docs=c.n_docs, nnz=c.nnz, tokens=c.n_tokens,
+                    parallelism=f"documents sharded by nnz over {world_} GPU(s)",
+                    l2="inputs (CSR + E + gamma + stats > 1 GB per GPU) exceed the 126 MB L2; no flush")
+
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample: the head of the same corpus, generated at a reduced document count
+        # The CPU arm: the oracle's restatement of the reference's own algorithm (log-space
+        # updatePhi, 99 sweeps) on every host core this process may use, each step over a bounded
+        # sample = the first n documents of the SAME corpus object the GPU arm runs on (same
+        # generator, seed and size; generated on cuda:0 when a GPU is present because the 1M-document
+        # sampler takes minutes on the CPU, otherwise the head of the document range is generated
+        # on the CPU with the same seed and the line says so).
         from oracle import oracle as O
-        sample_docs = min(wl["D"], 4096)
-        c = corpus.generate(sample_docs, V, K, mean_len, seed=list(corpus.SHAPES).index(args.workload) + 1,
-                            heavy_tail=corpus.SHAPES[args.workload][4])
+        cores = O.set_num_threads()
+        t_gen = time.perf_counter()
+        if torch.cuda.is_available():
+            full = corpus.generate(wl["D"], V, K, mean_len, seed=seed, heavy_tail=heavy, device="cuda:0")
+            torch.cuda.empty_cache()
+            origin = "the first {n} documents of the same corpus object (full.slice_docs)"
+        else:
+            full = corpus.generate(min(wl["D"], 4096), V, K, mean_len, seed=seed, heavy_tail=heavy)
+            origin = "the first {n} of a 4096-document corpus from the same generator and seed (no GPU to generate the full one)"
+        t_gen = time.perf_counter() - t_gen
         lb = corpus.init_logbeta(V, K, seed=7)
         alpha = np.full(K, 1e-3)
-        cores = O.num_threads()
-        rate, cores, n, ntok, dt = cpu_reference_rate(c, lb, alpha, target_s=8.0)
-        sub = c.slice_docs(0, n)
-        for _ in range(max(args.warmup, 0) and 1):
+        rate, cores, n, ntok, dt = cpu_reference_rate(full, lb, alpha, target_s=8.0)
+        sub = full.slice_docs(0, n)
+        for _ in range(1 if args.warmup > 0 else 0):
             O.estep(K, sub.row_ptr, sub.term_id, sub.count, lb, alpha)
         t0 = time.perf_counter()
         for _ in range(args.steps):
             O.estep(K, sub.row_ptr, sub.term_id, sub.count, lb, alpha)
         dt = (time.perf_counter() - t0) / args.steps
         val = sub.n_tokens / dt
-        sample = f"{n} documents / {sub.n_tokens} tokens of the {args.workload}-shape corpus per step"
+        sample = origin.format(n=n) + f", {sub.n_tokens} tokens per step"
+        cfg_full = config_of(full, world) if full.n_docs == wl["D"] else dict(wl, parallelism="host cores")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": wl,
+            "data": "synthetic", "config": cfg_full, "corpus_gen_s": round(t_gen, 2),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": sample,
                              "note": "CPU restatement of Mr.LDA's path (Hadoop LocalJobRunner unavailable: no JVM)"},
@@ -185,9 +205,8 @@ def main():
         dist.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world)
 
     from mrlda_b200 import capi
-    seed = list(corpus.SHAPES).index(args.workload) + 1
     t_gen = time.perf_counter()
-    full = corpus.generate(wl["D"], V, K, mean_len, seed=seed, heavy_tail=corpus.SHAPES[args.workload][4],
+    full = corpus.generate(wl["D"], V, K, mean_len, seed=seed, heavy_tail=heavy,
                            device=f"cuda:{local_rank}")
     torch.cuda.empty_cache()
     t_gen = time.perf_counter() - t_gen
@@ -253,7 +272,7 @@ def main():
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = max(1, args.steps)
         for _ in range(n_e2e):
             e2e_step()
         barrier()
@@ -286,6 +305,29 @@ def main():
     h2d_tot = allsum(e2e["h2d"]) if e2e else 0
     d2h_tot = allsum(e2e["d2h"]) if e2e else 0
 
+    # ---- after the timed regions: what the exchange produced, for the N = 1/2/4/8 lines to agree on.
+    # stats_sum: the K x V statistics after exchange() must add up to the corpus's token count
+    # (sum_k phi = 1); then one M-step (finalize + alpha) from those statistics and a checksum of the
+    # new logbeta / alpha.  Every rank holds the same replica; rank 0 reports.
+    check = None
+    if True:
+        stats = ctx.get_stats()
+        ssum = float(stats.sum(dtype=np.float64))
+        del stats
+        mres = ctx.m_step()
+        dl, nm, pr = ctx.get_beta()
+        seen = pr.astype(bool)
+        new_lb = ctx.get_logbeta()[seen]
+        wts = 1.0 + (np.arange(new_lb.shape[1], dtype=np.float64) % 7.0)
+        check = {"stats_sum": ssum, "stats_sum_rel_err": abs(ssum - total_tokens) / total_tokens,
+                 "terms_seen": int(seen.sum()),
+                 "logbeta_sum": float(new_lb.sum(dtype=np.float64)),
+                 "logbeta_weighted_sum": float((new_lb * wts[None, :]).sum(dtype=np.float64)),
+                 "normaliser_sum": float(nm.astype(np.float64).sum()),
+                 "alpha_sum": float(ctx.get_alpha().sum()),
+                 "m_step_ms": mres["m_step_ms"], "alpha_ms": mres["alpha_ms"]}
+        del dl, new_lb
+
     fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -313,10 +355,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 tile / f64 elsewhere (optional mode)" if args.fp32 else "f64",
             "data": "synthetic",
-            "config": dict(wl, docs=full.n_docs, nnz=full.nnz, tokens=total_tokens,
-                           parallelism=f"documents sharded by nnz over {world} GPU(s)",
-                           l2="inputs (CSR + E + gamma + stats > 1 GB per GPU) exceed the 126 MB L2; no flush",
-                           corpus_gen_s=round(t_gen, 2)),
+            "config": config_of(full, world), "corpus_gen_s": round(t_gen, 2),
             "device_ms_per_step": dev_ms_max / args.steps,
             "k1_ms": k1_ms_max, "allreduce_ms": ar_ms_max,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s",
@@ -335,6 +374,8 @@ def main():
             "slow_path_rows": results[-1]["slow_path_rows"],
             "log_likelihood": results[-1]["log_likelihood"],
         }
+        if check:
+            out["exchange_check"] = check
         if e2e:
             out["e2e"] = {"value": total_tokens / e2e_wall_max, "unit": UNIT,
                           "h2d_bytes_per_step": int(h2d_tot), "d2h_bytes_per_step": int(d2h_tot),

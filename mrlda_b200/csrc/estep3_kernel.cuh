@@ -170,6 +170,7 @@ struct Estep3Warp {
 template <int L, int KPL, int R, int NW, int NTM, int NSM>
 __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW> &w,
                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
+                                                  const double mycnt, const int lane,
                                                   double (&s)[KPL], unsigned &badbits) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int RPB = S::RPB, HALF = S::HALF, T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
@@ -252,43 +253,55 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
       pr[R + NTM + m] = (a0 + a1) + (a2 + a3);
     }
   }
-  // ---- norms (L-lane butterflies), r = n_w / norm_w: every step runs over all batches ----
+  // ---- norms and r = n_w / norm_w.  The L lanes of a row hold L partial sums for each of the NA
+  // batches.  A reduce-scatter (lane bit b keeps the odd or the even half and sends the other one)
+  // leaves lane j with the complete norm of batch j after NA (1 - 1/L) exchanges instead of
+  // NA log2(L); every lane then needs ONE reciprocal (not NA), and the NA values of r come back
+  // with one shuffle each.  Batches beyond the first L (NA = 9) take a plain butterfly. ----
   if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // pass B's first load, behind the chains
-#pragma unroll
-  for (int o = 1; o < L; o <<= 1) {
-#pragma unroll
-    for (int i = 0; i < NA; i++) pr[i] += __shfl_xor_sync(0xffffffffu, pr[i], o);
-  }
-  int minhi = 0x7fffffff;
-  {
-    double y[NA], t1[NA];
-#pragma unroll
-    for (int i = 0; i < NA; i++) {
-      asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(pr[i]));
-      minhi = min(minhi, __double2hiint(pr[i]));
-    }
-#pragma unroll
-    for (int i = 0; i < NA; i++) t1[i] = fma(-pr[i], y[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < NA; i++) y[i] = fma(y[i], t1[i], y[i]);
-#pragma unroll
-    for (int i = 0; i < NA; i++) t1[i] = fma(-pr[i], y[i], 1.0);
-#pragma unroll
-    for (int i = 0; i < NA; i++) y[i] = fma(y[i], t1[i], y[i]);
-#pragma unroll
-    for (int i = 0; i < NA; i++) rr[i] = w.cnt_w[(i < R + NTM ? i : i - NTM + T) * RPB + g] * y[i];
-  }
+  constexpr int NS = NA < L ? NA : L;
   badbits = 0;
-  if (__any_sync(0xffffffffu, minhi < __double2hiint(MRLDA_NORM_TINY))) {
-    // some norm underflowed (rare): those rows contribute through the exact log-space redo
+  {
+    double q[L];
 #pragma unroll
-    for (int i = 0; i < NA; i++) {
-      if (!(pr[i] >= MRLDA_NORM_TINY)) {
-        const int slot = i < R + NTM ? i : i - NTM + T;
-        if (w.cnt_w[slot * RPB + g] > 0.0) badbits |= 1u << slot;
-        rr[i] = 0.0;
+    for (int i = 0; i < L; i++) q[i] = i < NS ? pr[i] : 1.0;
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) {
+      const bool up = (j & o) != 0;
+#pragma unroll
+      for (int m = 0; m < L / (2 * o); m++) {
+        if (2 * m * o < NS) {  // entry 2m still carries live batches (compile-time after unrolling)
+          const double send = up ? q[2 * m] : q[2 * m + 1];
+          const double keep = up ? q[2 * m + 1] : q[2 * m];
+          q[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
       }
     }
+    const double nrm = q[0];  // norm of batch j, row g (lanes j >= NS hold a dummy)
+    const bool live = mycnt > 0.0;
+    const bool ok = nrm >= MRLDA_NORM_TINY;
+    const double r = (live && ok) ? mycnt * rcp_fast(nrm) : 0.0;
+    const int base = lane & ~(L - 1);
+#pragma unroll
+    for (int i = 0; i < NS; i++) rr[i] = __shfl_sync(0xffffffffu, r, base + i);
+    const unsigned bm = __ballot_sync(0xffffffffu, live && !ok);
+    if (bm) {  // some norm underflowed (rare): those rows contribute through the exact log-space redo
+      const unsigned mine = bm >> base;
+#pragma unroll
+      for (int i = 0; i < NS; i++)
+        if ((mine >> i) & 1u) badbits |= 1u << (i < R + NTM ? i : i - NTM + T);
+    }
+  }
+#pragma unroll
+  for (int i = NS; i < NA; i++) {
+    double p = pr[i];
+#pragma unroll
+    for (int o = 1; o < L; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    const int slot = i < R + NTM ? i : i - NTM + T;
+    const double cn = w.cnt_w[slot * RPB + g];
+    const bool ok = p >= MRLDA_NORM_TINY;
+    rr[i] = (cn > 0.0 && ok) ? cn * rcp_fast(p) : 0.0;
+    if (__any_sync(0xffffffffu, cn > 0.0 && !ok) && cn > 0.0 && !ok) badbits |= 1u << slot;
   }
   // ---- pass B: S_c += r_w E_wc ----
 #pragma unroll
@@ -390,42 +403,43 @@ __device__ __forceinline__ void estep3_sweep_last(const EstepArgs &a, const Este
   }
 }
 
-// sum of the RPB * nw partial sums of column col that warps [w0, w0 + nw) published
-template <int L, int KPL>
-__device__ __forceinline__ double estep3_colsum(const double *spart, const int w0, const int nw, const int col) {
-  constexpr int RPB = 32 / L, HALF = KPL / 2;
+// sum of the RPB * G partial sums of column col that warps [w0, w0 + G) published: all loads in
+// flight at once, then a tree (G is a compile-time constant of the launch)
+template <int L, int KPL, int G>
+__device__ __forceinline__ double estep3_colsum(const double *spart, const int w0, const int col) {
+  constexpr int RPB = 32 / L, HALF = KPL / 2, N = RPB * G;
   const int i = (col >> 1) / L, jj = (col >> 1) % L;
   const double *p = spart + ((size_t)(w0 * HALF + i) * 32 + jj) * 2 + (col & 1);
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 2
-  for (int w2 = 0; w2 < nw; w2++) {
+  double v[N];
 #pragma unroll
-    for (int gg = 0; gg < RPB; gg++) {
-      const double v = p[(size_t)w2 * HALF * 64 + gg * L * 2];
-      if ((gg & 3) == 0) s0 += v;
-      else if ((gg & 3) == 1) s1 += v;
-      else if ((gg & 3) == 2) s2 += v;
-      else s3 += v;
-    }
+  for (int w2 = 0; w2 < G; w2++) {
+#pragma unroll
+    for (int gg = 0; gg < RPB; gg++) v[w2 * RPB + gg] = p[(size_t)w2 * HALF * 64 + gg * L * 2];
   }
-  return (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int n = N / 2; n >= 1; n >>= 1) {
+#pragma unroll
+    for (int x = 0; x < n; x++) v[x] += v[x + n];
+  }
+  return v[0];
 }
 
 // Per-group state in shared memory and the launch geometry of the group this thread belongs to.
 struct Estep3Group {
   double *spart, *theta_g, *gam_g, *gextra_g, *alpha_s;
-  int w0, G, gt, GT, bar_id, K;
+  int w0, gt, bar_id, K;
 };
 
 // column owners after a sweep that is not the last: gamma_c = alpha_c + theta_c S_c
 // (DocumentMapper.java:232-234) and the next theta_c = exp(digamma(gamma_c)), two columns at a time
-template <int L, int KPL>
+template <int L, int KPL, int G>
 __device__ __forceinline__ void estep3_update_gamma(const Estep3Group &q) {
-  for (int col = q.gt; col < q.K; col += 2 * q.GT) {
-    const int col2 = col + q.GT;
+  constexpr int GT = 32 * G;
+  for (int col = q.gt; col < q.K; col += 2 * GT) {
+    const int col2 = col + GT;
     const bool two = col2 < q.K;
-    const double s0 = estep3_colsum<L, KPL>(q.spart, q.w0, q.G, col);
-    const double s1 = estep3_colsum<L, KPL>(q.spart, q.w0, q.G, two ? col2 : col);
+    const double s0 = estep3_colsum<L, KPL, G>(q.spart, q.w0, col);
+    const double s1 = estep3_colsum<L, KPL, G>(q.spart, q.w0, two ? col2 : col);
     const double g0 = fma(q.theta_g[col], s0, q.alpha_s[col]) + q.gextra_g[col];
     const double g1 = two ? fma(q.theta_g[col2], s1, q.alpha_s[col2]) + q.gextra_g[col2] : 1.0;
     q.gextra_g[col] = 0.0;
@@ -442,31 +456,35 @@ __device__ __forceinline__ void estep3_update_gamma(const Estep3Group &q) {
 }
 
 // sweeps 1..I-1 of one document for a warp that holds NTM TMEM and NSM shared-memory batches
-template <int L, int KPL, int R, int NW, int NTM, int NSM>
+template <int L, int KPL, int R, int NW, int G, int NTM, int NSM>
 __device__ __forceinline__ void estep3_run_sweeps(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
                                                   const Estep3Group &q,
                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
                                                   double2 *spart_w, const int nb, const int64_t zrow0,
                                                   const int lane) {
-  constexpr int HALF = KPL / 2;
+  using S = Estep3Shape<L, KPL, R, NW>;
+  constexpr int HALF = KPL / 2, GT = 32 * G, NA = R + NTM + NSM;
+  // n_w of the (batch, row) whose norm this lane completes in the reduce-scatter: batch j, row g
+  const int myslot = w.j < R + NTM ? w.j : w.j - NTM + S::T;
+  const double mycnt = w.j < NA ? w.cnt_w[myslot * S::RPB + w.g] : 0.0;
   for (int sweep = 0; sweep < a.sweeps - 1; sweep++) {
     double s[KPL];
     unsigned badbits;
-    estep3_sweep_fast<L, KPL, R, NW, NTM, NSM>(w, e, s, badbits);
+    estep3_sweep_fast<L, KPL, R, NW, NTM, NSM>(w, e, mycnt, lane, s, badbits);
     if (__any_sync(0xffffffffu, badbits != 0))
       (void)estep3_slow_rows<L>(a.term_id + zrow0, a.count + zrow0, a.logbeta, nullptr, a.slow_rows, q.gam_g,
                                 q.gextra_g, q.K, nb, badbits, lane, false);
     // S partials of every lane as they are; the column owners sum them
 #pragma unroll
     for (int i = 0; i < HALF; i++) spart_w[(size_t)i * 32] = make_double2(s[2 * i], s[2 * i + 1]);
-    estep3_group_sync(q.bar_id, q.GT);  // B1: S partials (and slow-path contributions) complete
-    estep3_update_gamma<L, KPL>(q);
-    estep3_group_sync(q.bar_id, q.GT);  // B2: theta published
+    estep3_group_sync(q.bar_id, GT);  // B1: S partials (and slow-path contributions) complete
+    estep3_update_gamma<L, KPL, G>(q);
+    estep3_group_sync(q.bar_id, GT);  // B2: theta published
   }
 }
 
 // picks the specialisation for this warp's batch count (once per document)
-template <int L, int KPL, int R, int NW, int NB_>
+template <int L, int KPL, int R, int NW, int G, int NB_>
 __device__ __forceinline__ void estep3_dispatch(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
                                                 const Estep3Group &q,
                                                 const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
@@ -476,16 +494,16 @@ __device__ __forceinline__ void estep3_dispatch(const EstepArgs &a, const Estep3
   constexpr int NTM = NB_ > R ? (NB_ - R < S::T ? NB_ - R : S::T) : 0;
   constexpr int NSM = NB_ > R + S::T ? NB_ - R - S::T : 0;
   if constexpr (NB_ >= S::NBMAX) {
-    estep3_run_sweeps<L, KPL, R, NW, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
+    estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
   } else {
     if (nb <= NB_)
-      estep3_run_sweeps<L, KPL, R, NW, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
+      estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
     else
-      estep3_dispatch<L, KPL, R, NW, NB_ + 1>(a, w, q, e, spart_w, nb, zrow0, lane);
+      estep3_dispatch<L, KPL, R, NW, G, NB_ + 1>(a, w, q, e, spart_w, nb, zrow0, lane);
   }
 }
 
-template <int L, int KPL, int R, int NW>
+template <int L, int KPL, int R, int NW, int G>
 __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int RPB = S::RPB, KS = S::KS, HALF = S::HALF, TW = S::TW, T = S::T, NBMAX = S::NBMAX;
@@ -494,7 +512,8 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int K = a.K;
-  const int G = a.group_warps, M = a.smem_batches;
+  const int M = a.smem_batches;
+  constexpr int GT = 32 * G;
   const int grp = warp / G, gw = warp % G;
   const Estep3Smem<L, KPL, R, NW> lay(M, G);
 
@@ -512,9 +531,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   q.gextra_g = smem + lay.gextra + (size_t)grp * KS;
   q.alpha_s = smem + lay.alpha;
   q.w0 = grp * G;
-  q.G = G;
   q.gt = gw * 32 + lane;
-  q.GT = 32 * G;
   q.bar_id = 1 + grp;
   q.K = K;
   w.theta2 = reinterpret_cast<const double2 *>(q.theta_g);
@@ -541,9 +558,9 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   const double lik_alpha = *a.lik_alpha;
 
   for (;;) {
-    estep3_group_sync(q.bar_id, q.GT);  // everybody is done with the previous document's shared state
+    estep3_group_sync(q.bar_id, GT);  // everybody is done with the previous document's shared state
     if (q.gt == 0) meta_s[1 + grp] = a.doc_begin + atomicAdd(a.work_counter, 1);
-    estep3_group_sync(q.bar_id, q.GT);
+    estep3_group_sync(q.bar_id, GT);
     const int qi = meta_s[1 + grp];
     if (qi >= a.doc_end) break;
     const int d = a.doc_order[qi];
@@ -601,17 +618,17 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
     // gamma start (DocumentMapper.java:184-193) and the first theta, by the column owners
     {
       const double share = (double)((float)a.doc_tokens[d] / (float)K);
-      for (int col = q.gt; col < K; col += q.GT) {
+      for (int col = q.gt; col < K; col += GT) {
         const double gam = a.use_stored_gamma ? a.gamma[(size_t)d * K + col] : q.alpha_s[col] + share;
         q.gam_g[col] = gam;
         q.theta_g[col] = exp_digamma(gam);
       }
     }
-    estep3_group_sync(q.bar_id, q.GT);
+    estep3_group_sync(q.bar_id, GT);
 
     // a warp without rows (short document, more warps than batches) still takes part in the barriers
     // ---- sweeps 1..I-1: loop body specialised on this warp's batch count ----
-    estep3_dispatch<L, KPL, R, NW, (R > 1 ? R : 1)>(a, w, q, e, spart_w, nb, zrow0, lane);
+    estep3_dispatch<L, KPL, R, NW, G, (R > 1 ? R : 1)>(a, w, q, e, spart_w, nb, zrow0, lane);
 
     // ---- last sweep, document epilogue (DocumentMapper.java:244-259,342-346) ----
     {
@@ -626,10 +643,10 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
       for (int i = 0; i < HALF; i++) spart_w[(size_t)i * 32] = make_double2(s[2 * i], s[2 * i + 1]);
       lik = warp_sum(lik);
       if (lane == 0) red_s[warp * 4 + 3] = lik;
-      estep3_group_sync(q.bar_id, q.GT);
+      estep3_group_sync(q.bar_id, GT);
       double sg = 0.0, lg = 0.0, lk = 0.0;
-      for (int col = q.gt; col < K; col += q.GT) {
-        const double sk = estep3_colsum<L, KPL>(q.spart, q.w0, G, col);
+      for (int col = q.gt; col < K; col += GT) {
+        const double sk = estep3_colsum<L, KPL, G>(q.spart, q.w0, col);
         const double add = q.theta_g[col] * sk;
         const double g_old = q.gam_g[col];
         const double g_new = q.alpha_s[col] + add + q.gextra_g[col];
@@ -648,7 +665,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
         red_s[warp * 4 + 1] = lg;
         red_s[warp * 4 + 2] = lk;
       }
-      estep3_group_sync(q.bar_id, q.GT);
+      estep3_group_sync(q.bar_id, GT);
       double tg = 0.0, tl = 0.0, tk = 0.0;
       for (int w2 = 0; w2 < G; w2++) {
         const double *rp = red_s + (q.w0 + w2) * 4;
@@ -657,7 +674,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
         tk += rp[2] + rp[3];
       }
       const double dsg = digamma_literal(tg);
-      for (int col = q.gt; col < K; col += q.GT) atomicAdd(ssacc_s + col, digamma_literal(q.gam_g[col]) - dsg);
+      for (int col = q.gt; col < K; col += GT) atomicAdd(ssacc_s + col, digamma_literal(q.gam_g[col]) - dsg);
       if (q.gt == 0) {
         const double ll = lik_alpha + (tl - lgamma(tg)) + tk;
         const long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254
@@ -679,7 +696,7 @@ struct Estep3Variant {
   int L, KPL, R, T, NW, MMAX;
   cudaError_t (*launch)(const EstepArgs &, int grid, int G, int M, size_t smem, cudaStream_t);
   size_t (*smem_bytes)(int M, int G);
-  cudaError_t (*prepare)(size_t smem);
+  cudaError_t (*prepare)(size_t smem, int G);
 };
 
 template <int L, int KPL, int R, int NW>
@@ -687,15 +704,28 @@ static size_t variant3_smem(int M, int G) {
   return Estep3Smem<L, KPL, R, NW>(M, G).total;
 }
 template <int L, int KPL, int R, int NW>
-static cudaError_t variant3_prepare(size_t smem) {
-  return cudaFuncSetAttribute(estep3_kernel<L, KPL, R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+static cudaError_t variant3_prepare(size_t smem, int G) {
+  const int sz = (int)smem;
+  switch (G) {
+    case 8: return cudaFuncSetAttribute(estep3_kernel<L, KPL, R, NW, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+    case 4: return cudaFuncSetAttribute(estep3_kernel<L, KPL, R, NW, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+    case 2: return cudaFuncSetAttribute(estep3_kernel<L, KPL, R, NW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+    case 1: return cudaFuncSetAttribute(estep3_kernel<L, KPL, R, NW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sz);
+  }
+  return cudaErrorInvalidValue;
 }
 template <int L, int KPL, int R, int NW>
 static cudaError_t variant3_launch(const EstepArgs &args, int grid, int G, int M, size_t smem, cudaStream_t st) {
   EstepArgs a = args;
   a.group_warps = G;
   a.smem_batches = M;
-  estep3_kernel<L, KPL, R, NW><<<grid, NW * 32, smem, st>>>(a);
+  switch (G) {
+    case 8: estep3_kernel<L, KPL, R, NW, 8><<<grid, NW * 32, smem, st>>>(a); break;
+    case 4: estep3_kernel<L, KPL, R, NW, 4><<<grid, NW * 32, smem, st>>>(a); break;
+    case 2: estep3_kernel<L, KPL, R, NW, 2><<<grid, NW * 32, smem, st>>>(a); break;
+    case 1: estep3_kernel<L, KPL, R, NW, 1><<<grid, NW * 32, smem, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
   return cudaGetLastError();
 }
 
@@ -708,7 +738,5 @@ static cudaError_t variant3_launch(const EstepArgs &args, int grid, int G, int M
 
 extern const Estep3Variant g_estep3_variants_L8[];
 extern const int g_estep3_variants_L8_n;
-extern const Estep3Variant g_estep3_variants_L8b[];
-extern const int g_estep3_variants_L8b_n;
 
 }  // namespace mrlda

@@ -56,6 +56,22 @@ int mrlda_oracle_num_threads(void) {
 #endif
 }
 
+/* Sets the OpenMP team size explicitly (bench.py passes the number of cores the process may run
+ * on): torchrun exports OMP_NUM_THREADS=1, which would otherwise turn the timed CPU arm into a
+ * single-thread run.  Returns the team size now in effect. */
+int mrlda_oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) {
+    omp_set_dynamic(0);
+    omp_set_num_threads(n);
+  }
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
+}
+
 /* cloud9 Gamma.digamma as pinned by VariationalInferenceTest (lda-c series). */
 #pragma GCC push_options
 #pragma GCC optimize("fp-contract=off")

@@ -45,6 +45,8 @@ def lib():
         L.mrlda_oracle_logadd.argtypes = [C.c_double, C.c_double]
         L.mrlda_oracle_set_logadd_cutoff.argtypes = [C.c_double]
         L.mrlda_oracle_num_threads.restype = C.c_int
+        L.mrlda_oracle_set_num_threads.restype = C.c_int
+        L.mrlda_oracle_set_num_threads.argtypes = [C.c_int]
         L.mrlda_oracle_update_scalar_alpha.restype = C.c_double
         L.mrlda_oracle_update_scalar_alpha.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double]
         L.mrlda_oracle_update_vector_alpha.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp]
@@ -91,6 +93,14 @@ def set_logadd_cutoff(nats):
 
 def num_threads():
     return lib().mrlda_oracle_num_threads()
+
+
+def set_num_threads(n=None):
+    """OpenMP team size; default = the cores this process may run on (ignores OMP_NUM_THREADS,
+    which torchrun sets to 1)."""
+    if n is None:
+        n = len(os.sched_getaffinity(0))
+    return lib().mrlda_oracle_set_num_threads(int(n))
 
 
 def update_vector_alpha(K, n_docs, alpha, ss):

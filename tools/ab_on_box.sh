@@ -12,10 +12,11 @@ cd "$(dirname "$0")/.."
 for name in "$@"; do
   cp "scratch_so/$name.so" mrlda_b200/libmrlda_b200.so || exit 1
   echo "== $name"
+  timeout 200 python tools/check3.py 200 2>&1 | tail -4 | cut -c1-150
   for r in "33 64" "97 128" "193 224"; do
     read -r lo hi <<<"$r"
     timeout 200 python tools/probe.py --docs 40000 --steps 3 --min-rows "$lo" --max-rows "$hi" 2>&1 | tail -1 | cut -c1-150
   done
   timeout 200 python tools/probe.py --docs 200000 --steps 3 2>&1 | tail -1 | cut -c1-150
 done
-timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
