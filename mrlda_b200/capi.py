@@ -280,7 +280,7 @@ class Context:
         return out.value
 
     def eval_special(self, which, x):
-        names = {"digamma": 0, "trigamma": 1, "lngamma": 2, "exp_digamma": 3}
+        names = {"digamma": 0, "trigamma": 1, "lngamma": 2, "exp_digamma": 3, "exp_digamma_n": 4}
         x = _arr(x, np.float64)
         y = np.empty_like(x)
         self._ck(load().mrlda_eval_special(self._h, names[which], x.size, x.ctypes.data_as(_dp),

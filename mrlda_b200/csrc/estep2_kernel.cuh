@@ -38,7 +38,11 @@
 #include "tmem_ops.cuh"
 
 #ifdef MRLDA_PHASE_TIMING
-#define MRLDA_TICK(i) tm[i] = clock64()
+#define MRLDA_TICK(i)                    \
+  do {                                   \
+    asm volatile("" ::: "memory");       \
+    tm[i] = clock64();                   \
+  } while (0)
 // tick that issues only after the value is available (a scoreboard dependency on its register)
 #define MRLDA_TICK_DEP(i, v)                                          \
   do {                                                                \

@@ -67,6 +67,14 @@ struct Estep3Shape {
   static_assert(NW == 8 || NW == 12 || NW == 16, "NW in {8, 12, 16}");
 };
 
+// the split of a warp's NA batches into the two halves of a sweep: the first one ends with or after
+// the register batches (their dot products are computed together)
+template <int R, int NA>
+struct Estep3Halves {
+  static constexpr int HALFUP = (NA + 1) / 2;
+  static constexpr int N1 = NA <= R ? NA : (HALFUP > R ? HALFUP : R);
+};
+
 // shared-memory carve-up (offsets in doubles) for M shared-memory batches per warp, groups of G warps
 template <int L, int KPL, int R, int NW>
 struct Estep3Smem {
@@ -76,7 +84,7 @@ struct Estep3Smem {
     const int NG = NW / G;
     size_t o = 0;
     tile = o;   o += (size_t)NW * M * 32 * KPL;
-    spart = o;  o += (size_t)NW * 32 * KPL;   // every lane's S partials: [warp][i][lane] double2
+    spart = o;  o += (size_t)NW * S::KS;      // every warp's column sums of S: [warp][column]
     theta = o;  o += (size_t)NG * S::KS;
     gam = o;    o += (size_t)NG * S::KS;
     gextra = o; o += (size_t)NG * S::KS;
@@ -164,22 +172,67 @@ struct Estep3Warp {
   int g, j;                // row of the batch / column group this lane works on
 };
 
+// Norms and r = n_w / norm_w of the batches [START, START + NSV) of a warp (NSV <= L).  The L lanes
+// of a row hold L partial sums for each batch.  A reduce-scatter (lane bit b keeps the odd or the
+// even half and sends the other one) leaves lane j with the complete norm of batch START + j after
+// NSV (1 - 1/L) exchanges instead of NSV log2(L); every lane then needs ONE reciprocal, and the NSV
+// values of r come back with one shuffle each.  mycnt is n_w of the (batch, row) this lane
+// completes (0 for padding rows and for lanes j >= NSV).
+template <int L, int NA, int START, int NSV, int RT, int NTM, int T>
+__device__ __forceinline__ void estep3_norm_exchange(const double (&pr)[NA], double (&rr)[NA], const double mycnt,
+                                                     const int j, const int lane, unsigned &badbits) {
+  static_assert(NSV >= 1 && NSV <= L && START + NSV <= NA, "one batch per lane of a row");
+  double q[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) q[i] = i < NSV ? pr[START + (i < NSV ? i : 0)] : 1.0;
+#pragma unroll
+  for (int o = 1; o < L; o <<= 1) {
+    const bool up = (j & o) != 0;
+#pragma unroll
+    for (int m = 0; m < L / (2 * o); m++) {
+      if (2 * m * o < NSV) {  // entry 2m still carries live batches (compile-time after unrolling)
+        const double send = up ? q[2 * m] : q[2 * m + 1];
+        const double keep = up ? q[2 * m + 1] : q[2 * m];
+        q[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+  }
+  const double nrm = q[0];  // norm of batch START + j, row g (lanes j >= NSV hold a dummy)
+  const bool live = mycnt > 0.0;
+  const bool ok = nrm >= MRLDA_NORM_TINY;
+  const double r = (live && ok) ? mycnt * rcp_fast(nrm) : 0.0;
+  const int base = lane & ~(L - 1);
+#pragma unroll
+  for (int i = 0; i < NSV; i++) rr[START + i] = __shfl_sync(0xffffffffu, r, base + i);
+  const unsigned bm = __ballot_sync(0xffffffffu, live && !ok);
+  if (bm) {  // some norm underflowed (rare): those rows contribute through the exact log-space redo
+    const unsigned mine = bm >> base;
+#pragma unroll
+    for (int i = 0; i < NSV; i++)
+      if ((mine >> i) & 1u) badbits |= 1u << (START + i < RT + NTM ? START + i : START + i - NTM + T);
+  }
+}
+
 // One of the sweeps 1..I-1 over the batches of this warp: NTM TMEM and NSM shared-memory batches
 // in use (compile time), so the whole sweep is straight-line code.  Returns S in s, the underflow
-// flags in badbits.
+// flags in badbits.  The batches are handled as two halves, [0, N1) and [N1, NA): the norm exchange
+// of the first half (shuffles, one reciprocal: a long dependent chain) is in flight behind the dot
+// products of the second half, and the exchange of the second half behind pass B of the first.
 template <int L, int KPL, int R, int NW, int NTM, int NSM>
 __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW> &w,
                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
-                                                  const double mycnt, const int lane,
-                                                  double (&s)[KPL], unsigned &badbits) {
+                                                  const double mycnt1, const double mycnt2, const int lane,
+                                                  double (&s)[KPL], unsigned &badbits, long long (&tm)[8]) {
   using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int RPB = S::RPB, HALF = S::HALF, T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
+  constexpr int HALF = S::HALF, T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
   constexpr int NA = R + NTM + NSM;  // batches in use; batch i < R + NTM sits in slot i, the others in slot i - NTM + T
-  static_assert(NA > 0, "a warp that takes part in a document holds at least one batch");
+  constexpr int N1 = Estep3Halves<R, NA>::N1, N2 = NA - N1;
+  static_assert(NA > 0 && N1 <= L && N2 <= L, "a warp holds between one and 2 L batches");
   double pr[NA];  // partial dot products -> norms
   double rr[NA];  // r_w = n_w / norm_w
-  const int g = w.g, j = w.j;
+  const int j = w.j;
   uint32_t wa[2 * CA], wb[2 * CB];
+  badbits = 0;
   // ---- pass A: theta in registers; partial dot products of every batch ----
   {
     double th[KPL];
@@ -189,6 +242,7 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
       th[2 * i] = v.x;
       th[2 * i + 1] = v.y;
     }
+    MRLDA_TICK_DEP(1, th[KPL - 1]);
     if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // in flight behind the register batches
     if constexpr (R > 0) {
       double acc[S::RA][4];
@@ -208,6 +262,8 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
       }
 #pragma unroll
       for (int q = 0; q < R; q++) pr[q] = (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
+      if constexpr (N1 == R)
+        estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
     }
 #pragma unroll
     for (int t = 0; t < NTM; t++) {
@@ -234,6 +290,8 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
         }
       }
       pr[R + t] = (a0 + a1) + (a2 + a3);
+      if (R + t == N1 - 1 && N1 > R)
+        estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
     }
 #pragma unroll
     for (int m = 0; m < NSM; m++) {
@@ -251,58 +309,14 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
         }
       }
       pr[R + NTM + m] = (a0 + a1) + (a2 + a3);
+      if (R + NTM + m == N1 - 1 && N1 > R)
+        estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
     }
   }
-  // ---- norms and r = n_w / norm_w.  The L lanes of a row hold L partial sums for each of the NA
-  // batches.  A reduce-scatter (lane bit b keeps the odd or the even half and sends the other one)
-  // leaves lane j with the complete norm of batch j after NA (1 - 1/L) exchanges instead of
-  // NA log2(L); every lane then needs ONE reciprocal (not NA), and the NA values of r come back
-  // with one shuffle each.  Batches beyond the first L (NA = 9) take a plain butterfly. ----
+  MRLDA_TICK_DEP(2, pr[NA - 1]);
   if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // pass B's first load, behind the chains
-  constexpr int NS = NA < L ? NA : L;
-  badbits = 0;
-  {
-    double q[L];
-#pragma unroll
-    for (int i = 0; i < L; i++) q[i] = i < NS ? pr[i] : 1.0;
-#pragma unroll
-    for (int o = 1; o < L; o <<= 1) {
-      const bool up = (j & o) != 0;
-#pragma unroll
-      for (int m = 0; m < L / (2 * o); m++) {
-        if (2 * m * o < NS) {  // entry 2m still carries live batches (compile-time after unrolling)
-          const double send = up ? q[2 * m] : q[2 * m + 1];
-          const double keep = up ? q[2 * m + 1] : q[2 * m];
-          q[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-      }
-    }
-    const double nrm = q[0];  // norm of batch j, row g (lanes j >= NS hold a dummy)
-    const bool live = mycnt > 0.0;
-    const bool ok = nrm >= MRLDA_NORM_TINY;
-    const double r = (live && ok) ? mycnt * rcp_fast(nrm) : 0.0;
-    const int base = lane & ~(L - 1);
-#pragma unroll
-    for (int i = 0; i < NS; i++) rr[i] = __shfl_sync(0xffffffffu, r, base + i);
-    const unsigned bm = __ballot_sync(0xffffffffu, live && !ok);
-    if (bm) {  // some norm underflowed (rare): those rows contribute through the exact log-space redo
-      const unsigned mine = bm >> base;
-#pragma unroll
-      for (int i = 0; i < NS; i++)
-        if ((mine >> i) & 1u) badbits |= 1u << (i < R + NTM ? i : i - NTM + T);
-    }
-  }
-#pragma unroll
-  for (int i = NS; i < NA; i++) {
-    double p = pr[i];
-#pragma unroll
-    for (int o = 1; o < L; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    const int slot = i < R + NTM ? i : i - NTM + T;
-    const double cn = w.cnt_w[slot * RPB + g];
-    const bool ok = p >= MRLDA_NORM_TINY;
-    rr[i] = (cn > 0.0 && ok) ? cn * rcp_fast(p) : 0.0;
-    if (__any_sync(0xffffffffu, cn > 0.0 && !ok) && cn > 0.0 && !ok) badbits |= 1u << slot;
-  }
+  if constexpr (N2 > 0) estep3_norm_exchange<L, NA, N1, (N2 > 0 ? N2 : 1), R, NTM, T>(pr, rr, mycnt2, j, lane, badbits);
+  MRLDA_TICK_DEP(3, rr[0]);
   // ---- pass B: S_c += r_w E_wc ----
 #pragma unroll
   for (int c = 0; c < KPL; c++) s[c] = 0.0;
@@ -403,21 +417,49 @@ __device__ __forceinline__ void estep3_sweep_last(const EstepArgs &a, const Este
   }
 }
 
-// sum of the RPB * G partial sums of column col that warps [w0, w0 + G) published: all loads in
-// flight at once, then a tree (G is a compile-time constant of the launch)
-template <int L, int KPL, int G>
-__device__ __forceinline__ double estep3_colsum(const double *spart, const int w0, const int col) {
-  constexpr int RPB = 32 / L, HALF = KPL / 2, N = RPB * G;
-  const int i = (col >> 1) / L, jj = (col >> 1) % L;
-  const double *p = spart + ((size_t)(w0 * HALF + i) * 32 + jj) * 2 + (col & 1);
-  double v[N];
+// S exchange, first half.  After pass B lane (g, j) holds the partial sums of its 26 columns over
+// its own rows.  A two-level reduce-scatter over the warp's four row groups (lane bits 4 and 3)
+// leaves every lane with the WARP's sums of 7 or 6 of those columns: level one keeps the x or the y
+// element of each column pair, level two the lower or the upper half of the pairs.  20 exchanges
+// instead of 26 stores per lane, and the column owners then read G values per column, not 4 G.
+template <int L, int KPL>
+__device__ __forceinline__ void estep3_publish_s(const double (&s)[KPL], double *wtot_w, const int lane) {
+  static_assert(L == 8, "the row-group reduce-scatter is written for four row groups per warp");
+  constexpr int HALF = KPL / 2, H2 = HALF / 2, LO = HALF - H2;
+  const bool up1 = (lane & 16) != 0, up2 = (lane & 8) != 0;
+  double v[HALF];
 #pragma unroll
-  for (int w2 = 0; w2 < G; w2++) {
-#pragma unroll
-    for (int gg = 0; gg < RPB; gg++) v[w2 * RPB + gg] = p[(size_t)w2 * HALF * 64 + gg * L * 2];
+  for (int m = 0; m < HALF; m++) {
+    const double send = up1 ? s[2 * m] : s[2 * m + 1];
+    const double keep = up1 ? s[2 * m + 1] : s[2 * m];
+    v[m] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
   }
+  double f[LO];
 #pragma unroll
-  for (int n = N / 2; n >= 1; n >>= 1) {
+  for (int m = 0; m < H2; m++) {
+    const double send = up2 ? v[m] : v[LO + m];
+    const double keep = up2 ? v[LO + m] : v[m];
+    f[m] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  if constexpr (LO > H2) f[H2] = v[H2] + __shfl_xor_sync(0xffffffffu, v[H2], 8);  // lower half only
+  // value m of this lane is column 2 (j + L (m + (up2 ? LO : 0))) + (up1 ? 1 : 0)
+  double *dst = wtot_w + 2 * (lane & (L - 1)) + (up1 ? 1 : 0) + (up2 ? 2 * L * LO : 0);
+#pragma unroll
+  for (int m = 0; m < H2; m++) dst[2 * L * m] = f[m];
+  if constexpr (LO > H2) {
+    if (!up2) dst[2 * L * H2] = f[H2];
+  }
+}
+
+// S exchange, second half: the sum of the G warp sums of column col
+template <int KS, int G>
+__device__ __forceinline__ double estep3_colsum(const double *wtot, const int w0, const int col) {
+  const double *p = wtot + (size_t)w0 * KS + col;
+  double v[G];
+#pragma unroll
+  for (int w2 = 0; w2 < G; w2++) v[w2] = p[(size_t)w2 * KS];
+#pragma unroll
+  for (int n = G / 2; n >= 1; n >>= 1) {
 #pragma unroll
     for (int x = 0; x < n; x++) v[x] += v[x + n];
   }
@@ -431,28 +473,49 @@ struct Estep3Group {
 };
 
 // column owners after a sweep that is not the last: gamma_c = alpha_c + theta_c S_c
-// (DocumentMapper.java:232-234) and the next theta_c = exp(digamma(gamma_c)), two columns at a time
-template <int L, int KPL, int G>
-__device__ __forceinline__ void estep3_update_gamma(const Estep3Group &q) {
-  constexpr int GT = 32 * G;
-  for (int col = q.gt; col < q.K; col += 2 * GT) {
-    const int col2 = col + GT;
-    const bool two = col2 < q.K;
-    const double s0 = estep3_colsum<L, KPL, G>(q.spart, q.w0, col);
-    const double s1 = estep3_colsum<L, KPL, G>(q.spart, q.w0, two ? col2 : col);
-    const double g0 = fma(q.theta_g[col], s0, q.alpha_s[col]) + q.gextra_g[col];
-    const double g1 = two ? fma(q.theta_g[col2], s1, q.alpha_s[col2]) + q.gextra_g[col2] : 1.0;
-    q.gextra_g[col] = 0.0;
-    q.gam_g[col] = g0;
-    const double t0 = exp_digamma(g0);
-    const double t1 = exp_digamma(g1);
-    q.theta_g[col] = t0;
-    if (two) {
-      q.gextra_g[col2] = 0.0;
-      q.gam_g[col2] = g1;
-      q.theta_g[col2] = t1;
+// (DocumentMapper.java:232-234) and the next theta_c = exp(digamma(gamma_c)).  A thread owns the
+// columns gt, gt + 32 G, ...; NW_ of them reach into [0, K) for this warp (warp-uniform).  They are
+// evaluated as interleaved chains (exp_digamma_n).
+template <int L, int KPL, int G, int NW_>
+__device__ __forceinline__ void estep3_update_gamma_n(const Estep3Group &q) {
+  constexpr int GT = 32 * G, KS = L * KPL;
+  double gv[NW_], tv[NW_];
+#pragma unroll
+  for (int x = 0; x < NW_; x++) {
+    const int col = q.gt + GT * x;
+    const int cc = col < q.K ? col : q.K - 1;
+    const double sk = estep3_colsum<KS, G>(q.spart, q.w0, cc);
+    gv[x] = fma(q.theta_g[cc], sk, q.alpha_s[cc]) + q.gextra_g[cc];
+  }
+  exp_digamma_n<NW_>(gv, tv);
+#pragma unroll
+  for (int x = 0; x < NW_; x++) {
+    const int col = q.gt + GT * x;
+    if (col < q.K) {
+      q.gextra_g[col] = 0.0;
+      q.gam_g[col] = gv[x];
+      q.theta_g[col] = tv[x];
     }
   }
+}
+template <int L, int KPL, int G, int NC_>
+__device__ __forceinline__ void estep3_update_gamma_pick(const Estep3Group &q, const int ncols) {
+  if constexpr (NC_ <= 1) {
+    estep3_update_gamma_n<L, KPL, G, 1>(q);
+  } else {
+    if (ncols >= NC_)
+      estep3_update_gamma_n<L, KPL, G, NC_>(q);
+    else
+      estep3_update_gamma_pick<L, KPL, G, NC_ - 1>(q, ncols);
+  }
+}
+template <int L, int KPL, int G>
+__device__ __forceinline__ void estep3_update_gamma(const Estep3Group &q) {
+  constexpr int GT = 32 * G, KS = L * KPL, NC = (KS + GT - 1) / GT;
+  const int wbase = q.gt & ~31;
+  if (wbase >= q.K) return;  // a warp whose columns all lie beyond K
+  const int ncols = (q.K - wbase + GT - 1) / GT;  // columns wbase + GT x < K
+  estep3_update_gamma_pick<L, KPL, G, NC>(q, ncols);
 }
 
 // sweeps 1..I-1 of one document for a warp that holds NTM TMEM and NSM shared-memory batches
@@ -460,26 +523,43 @@ template <int L, int KPL, int R, int NW, int G, int NTM, int NSM>
 __device__ __forceinline__ void estep3_run_sweeps(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
                                                   const Estep3Group &q,
                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
-                                                  double2 *spart_w, const int nb, const int64_t zrow0,
+                                                  double *wtot_w, const int nb, const int64_t zrow0,
                                                   const int lane) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int HALF = KPL / 2, GT = 32 * G, NA = R + NTM + NSM;
-  // n_w of the (batch, row) whose norm this lane completes in the reduce-scatter: batch j, row g
-  const int myslot = w.j < R + NTM ? w.j : w.j - NTM + S::T;
-  const double mycnt = w.j < NA ? w.cnt_w[myslot * S::RPB + w.g] : 0.0;
+  // n_w of the (batch, row) whose norm this lane completes in the two reduce-scatters: batches j and
+  // N1 + j, row g
+  constexpr int N1 = Estep3Halves<R, NA>::N1;
+  const int b2 = N1 + w.j;
+  const int slot1 = w.j < R + NTM ? w.j : w.j - NTM + S::T;
+  const int slot2 = b2 < R + NTM ? b2 : b2 - NTM + S::T;
+  const double mycnt1 = w.j < N1 ? w.cnt_w[slot1 * S::RPB + w.g] : 0.0;
+  const double mycnt2 = b2 < NA ? w.cnt_w[slot2 * S::RPB + w.g] : 0.0;
   for (int sweep = 0; sweep < a.sweeps - 1; sweep++) {
     double s[KPL];
     unsigned badbits;
-    estep3_sweep_fast<L, KPL, R, NW, NTM, NSM>(w, e, mycnt, lane, s, badbits);
+    long long tm[8];
+    (void)tm;
+    MRLDA_TICK(0);
+    estep3_sweep_fast<L, KPL, R, NW, NTM, NSM>(w, e, mycnt1, mycnt2, lane, s, badbits, tm);
+    MRLDA_TICK_DEP(4, s[KPL - 1]);
     if (__any_sync(0xffffffffu, badbits != 0))
       (void)estep3_slow_rows<L>(a.term_id + zrow0, a.count + zrow0, a.logbeta, nullptr, a.slow_rows, q.gam_g,
                                 q.gextra_g, q.K, nb, badbits, lane, false);
-    // S partials of every lane as they are; the column owners sum them
-#pragma unroll
-    for (int i = 0; i < HALF; i++) spart_w[(size_t)i * 32] = make_double2(s[2 * i], s[2 * i + 1]);
-    estep3_group_sync(q.bar_id, GT);  // B1: S partials (and slow-path contributions) complete
+    estep3_publish_s<L, KPL>(s, wtot_w, lane);
+    estep3_group_sync(q.bar_id, GT);  // B1: warp sums of S (and slow-path contributions) complete
+    MRLDA_TICK(5);
     estep3_update_gamma<L, KPL, G>(q);
+    MRLDA_TICK(6);
     estep3_group_sync(q.bar_id, GT);  // B2: theta published
+    MRLDA_TICK(7);
+#ifdef MRLDA_PHASE_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      for (int i = 0; i < 7; i++) a.phase_cycles[i] += tm[i + 1] - tm[i];
+      a.phase_cycles[7] += 1;
+      a.phase_cycles[8] += NA;
+    }
+#endif
   }
 }
 
@@ -488,18 +568,18 @@ template <int L, int KPL, int R, int NW, int G, int NB_>
 __device__ __forceinline__ void estep3_dispatch(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
                                                 const Estep3Group &q,
                                                 const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
-                                                double2 *spart_w, const int nb, const int64_t zrow0,
+                                                double *wtot_w, const int nb, const int64_t zrow0,
                                                 const int lane) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int NTM = NB_ > R ? (NB_ - R < S::T ? NB_ - R : S::T) : 0;
   constexpr int NSM = NB_ > R + S::T ? NB_ - R - S::T : 0;
   if constexpr (NB_ >= S::NBMAX) {
-    estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
+    estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, wtot_w, nb, zrow0, lane);
   } else {
     if (nb <= NB_)
-      estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, spart_w, nb, zrow0, lane);
+      estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, wtot_w, nb, zrow0, lane);
     else
-      estep3_dispatch<L, KPL, R, NW, G, NB_ + 1>(a, w, q, e, spart_w, nb, zrow0, lane);
+      estep3_dispatch<L, KPL, R, NW, G, NB_ + 1>(a, w, q, e, wtot_w, nb, zrow0, lane);
   }
 }
 
@@ -535,7 +615,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   q.bar_id = 1 + grp;
   q.K = K;
   w.theta2 = reinterpret_cast<const double2 *>(q.theta_g);
-  double2 *spart_w = reinterpret_cast<double2 *>(q.spart) + (size_t)warp * HALF * 32 + lane;
+  double *wtot_w = q.spart + (size_t)warp * KS;
   double *ssacc_s = smem + lay.ssacc;
   double *red_s = smem + lay.red;  // [warp][4]
   int *meta_s = reinterpret_cast<int *>(smem + lay.meta);  // [0] TMEM base, [1 + grp] document
@@ -628,7 +708,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
 
     // a warp without rows (short document, more warps than batches) still takes part in the barriers
     // ---- sweeps 1..I-1: loop body specialised on this warp's batch count ----
-    estep3_dispatch<L, KPL, R, NW, G, (R > 1 ? R : 1)>(a, w, q, e, spart_w, nb, zrow0, lane);
+    estep3_dispatch<L, KPL, R, NW, G, (R > 1 ? R : 1)>(a, w, q, e, wtot_w, nb, zrow0, lane);
 
     // ---- last sweep, document epilogue (DocumentMapper.java:244-259,342-346) ----
     {
@@ -639,14 +719,13 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
       if (__any_sync(0xffffffffu, badbits != 0))
         lik += estep3_slow_rows<L>(a.term_id + zrow0, a.count + zrow0, a.logbeta, a.learning ? a.stats : nullptr,
                                    a.slow_rows, q.gam_g, q.gextra_g, K, nb, badbits, lane, true);
-#pragma unroll
-      for (int i = 0; i < HALF; i++) spart_w[(size_t)i * 32] = make_double2(s[2 * i], s[2 * i + 1]);
+      estep3_publish_s<L, KPL>(s, wtot_w, lane);
       lik = warp_sum(lik);
       if (lane == 0) red_s[warp * 4 + 3] = lik;
       estep3_group_sync(q.bar_id, GT);
       double sg = 0.0, lg = 0.0, lk = 0.0;
       for (int col = q.gt; col < K; col += GT) {
-        const double sk = estep3_colsum<L, KPL, G>(q.spart, q.w0, col);
+        const double sk = estep3_colsum<KS, G>(q.spart, q.w0, col);
         const double add = q.theta_g[col] * sk;
         const double g_old = q.gam_g[col];
         const double g_new = q.alpha_s[col] + add + q.gextra_g[col];

@@ -338,6 +338,13 @@ __global__ void eval_special_kernel(int which, int64_t n, const double *x, doubl
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double v = x[i];
+  if (which == 4) {  // the interleaved short-chain form the warp-group kernel uses
+    const double in[2] = {v, v + 1.0};
+    double out[2];
+    exp_digamma_n<2>(in, out);
+    y[i] = out[0];
+    return;
+  }
   y[i] = which == 0 ? digamma_literal(v)
                     : which == 1 ? trigamma_literal(v) : which == 2 ? lgamma(v) : exp_digamma(v);
 }
@@ -1458,7 +1465,7 @@ int mrlda_update_scalar_alpha(mrlda_ctx *ctx, int32_t n_topics, int32_t n_docs, 
 }
 
 int mrlda_eval_special(mrlda_ctx *ctx, int32_t which, int64_t n, const double *x, double *y) {
-  if (!ctx || !x || !y || n < 0 || which < 0 || which > 3) return MRLDA_EINVAL;
+  if (!ctx || !x || !y || n < 0 || which < 0 || which > 4) return MRLDA_EINVAL;
   if (n == 0) return MRLDA_OK;
   CK(cudaSetDevice(ctx->cfg.device));
   double *buf = nullptr;

@@ -347,6 +347,7 @@ def test_device_special_functions_match_oracle(capi, oracle):
         tg = ctx.eval_special("trigamma", x)
         lg = ctx.eval_special("lngamma", x)
         ed = ctx.eval_special("exp_digamma", x)
+        edn = ctx.eval_special("exp_digamma_n", x)
     want_dg = np.array([oracle.digamma(v) for v in x])
     assert np.array_equal(dg, want_dg) or rel_err(dg, want_dg) < 1e-13
     assert rel_err(tg, [oracle.trigamma(v) for v in x]) < 1e-13
@@ -354,6 +355,10 @@ def test_device_special_functions_match_oracle(capi, oracle):
     assert np.max(np.abs(lg - lgw) / np.maximum(np.abs(lgw), 1.0)) < 1e-13
     big = x > 2e-3  # below, exp(digamma) underflows towards 0
     assert rel_err(ed[big], np.exp(want_dg[big])) < 1e-12
+    # the interleaved short-chain form of the warp-group kernel: same series, same zeros
+    assert rel_err(edn[big], np.exp(want_dg[big])) < 1e-12
+    assert rel_err(edn[big], ed[big]) < 1e-12  # |u| ulp(1): exp(u) amplifies the rounding of u near -500
+    assert np.all(edn[~big] >= 0.0) and np.all(edn[~big] < 1e-200)
 
 
 def test_all_documents_empty_and_no_documents(capi, oracle):

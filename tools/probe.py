@@ -46,7 +46,8 @@ def main():
         peak = ctx.measure_fp64_peak()
         ph = ctx.debug_phase_cycles()
     if ph[7]:
-        names = ['theta', 'dots', 'B1', 'norms', 'B2', 'S', 'RS']
+        names = (['thetaLDS', 'passA', 'norms', 'passB', 'pub+B1', 'gamma', 'B2'] if os.environ.get('MRLDA_ESTEP_KERNEL', '3') == '3'
+                 else ['theta', 'dots', 'B1', 'norms', 'B2', 'S', 'RS'])
         print('phase cycles per sweep (block 0, thread 0): ' + ', '.join(f'{n}={ph[i] / ph[7]:.0f}' for i, n in enumerate(names)) + f'  total={ph[:7].sum() / ph[7]:.0f}  slots/sweep={ph[8] / ph[7]:.2f}  expdigamma={ph[9] / ph[7]:.0f}')
     if ph[13]:
         print(f'per document (block 0): load={ph[10] / ph[13]:.0f} sweeps={ph[11] / ph[13]:.0f} '
