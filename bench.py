@@ -362,8 +362,9 @@ def main():
                          "frac": ach / hbm,
                          "traffic": measured_traffic(args.workload, world) if args.scale == 1.0 else None,
                          "peak_source": how,
-                         "kernel": "estep2_kernel<8,26,2,8> (+ estep_kernel<8,26> for documents above 320 rows)"
-                         if K == 200 else "estep2_kernel / estep_kernel",
+                         "kernel": "estep3_kernel<8,25,2,8,G>, one launch per document class (G = 8/4/2/1 warps "
+                                   "per document), + estep_kernel<8,26> for documents above 320 rows"
+                         if K == 200 else "estep3_kernel / estep2_kernel / estep_kernel",
                          "algorithmic_bytes_per_launch": B,
                          "note": "binding resource is the FP64 pipe, see fp64"},
             "fp64": {"achieved_tflops": F / (k1_ms_max * 1e-3) / 1e12, "peak_tflops": fp64_peak,

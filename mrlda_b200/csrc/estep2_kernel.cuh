@@ -110,6 +110,11 @@ __device__ __forceinline__ void tmem_ld_words(uint32_t addr, uint32_t *w) {
   } else if constexpr (W >= 4) {
     TmemVec<4>::ld(addr + OFF, *reinterpret_cast<uint32_t(*)[4]>(w + OFF));
     tmem_ld_words<W - 4, OFF + 4>(addr, w);
+  } else if constexpr (W >= 2) {
+    TmemVec<2>::ld(addr + OFF, *reinterpret_cast<uint32_t(*)[2]>(w + OFF));
+    tmem_ld_words<W - 2, OFF + 2>(addr, w);
+  } else {
+    static_assert(W == 0, "TMEM slots hold doubles: an even number of words");
   }
 }
 template <int W, int OFF = 0>
@@ -129,6 +134,11 @@ __device__ __forceinline__ void tmem_st_words(uint32_t addr, const uint32_t *w) 
   } else if constexpr (W >= 4) {
     TmemVec<4>::st(addr + OFF, *reinterpret_cast<const uint32_t(*)[4]>(w + OFF));
     tmem_st_words<W - 4, OFF + 4>(addr, w);
+  } else if constexpr (W >= 2) {
+    TmemVec<2>::st(addr + OFF, *reinterpret_cast<const uint32_t(*)[2]>(w + OFF));
+    tmem_st_words<W - 2, OFF + 2>(addr, w);
+  } else {
+    static_assert(W == 0, "TMEM slots hold doubles: an even number of words");
   }
 }
 

@@ -13,7 +13,10 @@
 //   * Inside a group ROWS are split across warps: warp k owns a contiguous range of row batches.
 //     A batch is RPB = 32/L rows; L lanes share a row, lane j of a row owns the KPL columns
 //     {2(j + L i), 2(j + L i) + 1}, i < KPL/2 (same column interleave as estep_kernel.cuh, so row
-//     loads and statistics atomics touch 16-byte units that are contiguous across the L lanes).
+//     loads and statistics atomics touch 16-byte units that are contiguous across the L lanes)
+//     and, when KPL is odd, the single column 2 L (KPL/2) + j: K = 200 is 8 lanes x 25 columns
+//     with no padding column, and a batch is 50 Tensor Memory words, so that five fit a warp's
+//     256 columns.
 //     Every warp therefore holds COMPLETE rows: norm_w needs only an L-lane butterfly (3 shuffle
 //     levels at K = 200) and r_w = n_w / norm_w is used by the same lanes right away — no CTA
 //     barrier and no shared-memory exchange per row.  S_c accumulates per lane over the warp's rows.
@@ -51,7 +54,8 @@ template <int L, int KPL, int R, int NW>
 struct Estep3Shape {
   static constexpr int RPB = 32 / L;
   static constexpr int KS = L * KPL;
-  static constexpr int HALF = KPL / 2;
+  static constexpr int HP = KPL / 2;                   // column pairs of a lane ...
+  static constexpr int ODD = KPL & 1;                  // ... and the single column of an odd KPL
   static constexpr int TW = 2 * KPL;                   // 32-bit TMEM columns per batch and lane
   static constexpr int WQ = NW / 4;                    // warps that share a TMEM lane quarter
   static constexpr int TWORDS = (512 / WQ) / 4 * 4;    // TMEM columns of one warp
@@ -62,7 +66,7 @@ struct Estep3Shape {
   static constexpr int CB = KPL - CA;                  // ... and by the second
   static constexpr int RA = R > 0 ? R : 1;             // extent of the register-batch array
   static constexpr int THREADS = NW * 32;
-  static_assert(KPL % 2 == 0 && KPL > CA && KPL <= 32, "KPL must be even, in (16, 32]");
+  static_assert(KPL > CA && KPL <= 32, "KPL in (16, 32]");
   static_assert(L == 1 || L == 2 || L == 4 || L == 8 || L == 16 || L == 32, "L must divide 32");
   static_assert(NW == 8 || NW == 12 || NW == 16, "NW in {8, 12, 16}");
 };
@@ -104,16 +108,58 @@ __device__ __forceinline__ double estep3_w2d(const uint32_t lo, const uint32_t h
   return __hiloint2double((int)hi, (int)lo);
 }
 
+// A lane's KPL values of a K-contiguous row (global or shared memory): HP 16-byte pairs and, for an
+// odd KPL, one more double.
+template <int L, int KPL, bool GLOBAL>
+__device__ __forceinline__ void estep3_load_cols(const double *row, const int j, double (&v)[KPL]) {
+  constexpr int HP = KPL / 2;
+  const double2 *src = reinterpret_cast<const double2 *>(row) + j;
+#pragma unroll
+  for (int i = 0; i < HP; i++) {
+    const double2 t2 = GLOBAL ? __ldg(src + L * i) : src[L * i];
+    v[2 * i] = t2.x;
+    v[2 * i + 1] = t2.y;
+  }
+  if constexpr (KPL & 1) v[KPL - 1] = GLOBAL ? __ldg(row + 2 * L * HP + j) : row[2 * L * HP + j];
+}
+// A batch of the thread-private, lane-interleaved shared-memory region: [HP][32] double2, [32] double
+template <int KPL>
+__device__ __forceinline__ void estep3_tile_ld(const double *batch, const int lane, double (&v)[KPL]) {
+  constexpr int HP = KPL / 2;
+  const double2 *src = reinterpret_cast<const double2 *>(batch) + lane;
+#pragma unroll
+  for (int i = 0; i < HP; i++) {
+    const double2 t2 = src[(size_t)i * 32];
+    v[2 * i] = t2.x;
+    v[2 * i + 1] = t2.y;
+  }
+  if constexpr (KPL & 1) v[KPL - 1] = batch[HP * 64 + lane];
+}
+template <int KPL>
+__device__ __forceinline__ void estep3_tile_st(double *batch, const int lane, const double (&v)[KPL]) {
+  constexpr int HP = KPL / 2;
+  double2 *dst = reinterpret_cast<double2 *>(batch) + lane;
+#pragma unroll
+  for (int i = 0; i < HP; i++) dst[(size_t)i * 32] = make_double2(v[2 * i], v[2 * i + 1]);
+  if constexpr (KPL & 1) batch[HP * 64 + lane] = v[KPL - 1];
+}
+
 // n_w phi_wk = r_w theta_k E_wk into the K x V statistics (DocumentMapper.java:315-329)
 template <int L, int KPL>
-__device__ __forceinline__ void estep3_scatter(double *srow, const double2 *theta2, const double r,
+__device__ __forceinline__ void estep3_scatter(double *srow, const double *theta_g, const double r,
                                                const double (&ev)[KPL], const int j, const int K) {
+  constexpr int HP = KPL / 2;
+  const double2 *theta2 = reinterpret_cast<const double2 *>(theta_g);
 #pragma unroll
-  for (int i = 0; i < KPL / 2; i++) {
+  for (int i = 0; i < HP; i++) {
     const double2 tv = theta2[j + L * i];
     const int col = 2 * (j + L * i);
     if (col < K) atomicAdd(srow + col, r * tv.x * ev[2 * i]);
     if (col + 1 < K) atomicAdd(srow + col + 1, r * tv.y * ev[2 * i + 1]);
+  }
+  if constexpr (KPL & 1) {
+    const int col = 2 * L * HP + j;
+    if (col < K) atomicAdd(srow + col, r * theta_g[col] * ev[KPL - 1]);
   }
 }
 
@@ -166,8 +212,8 @@ static __device__ __noinline__ double estep3_slow_rows(const int32_t *term_id, c
 template <int L, int KPL, int R, int NW>
 struct Estep3Warp {
   uint32_t tbase;          // this warp's TMEM slots
-  const double2 *tile2;    // this warp's shared-memory batches (+ lane)
-  const double2 *theta2;   // the group's theta as double2 pairs
+  const double *tile_w;    // this warp's shared-memory batches
+  const double *theta_g;   // the group's theta
   const double *cnt_w;     // n_w of this warp's batch slots (0 for padding rows)
   int g, j;                // row of the batch / column group this lane works on
 };
@@ -224,7 +270,7 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
                                                   const double mycnt1, const double mycnt2, const int lane,
                                                   double (&s)[KPL], unsigned &badbits, long long (&tm)[8]) {
   using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int HALF = S::HALF, T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
+  constexpr int T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
   constexpr int NA = R + NTM + NSM;  // batches in use; batch i < R + NTM sits in slot i, the others in slot i - NTM + T
   constexpr int N1 = Estep3Halves<R, NA>::N1, N2 = NA - N1;
   static_assert(NA > 0 && N1 <= L && N2 <= L, "a warp holds between one and 2 L batches");
@@ -236,12 +282,7 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
   // ---- pass A: theta in registers; partial dot products of every batch ----
   {
     double th[KPL];
-#pragma unroll
-    for (int i = 0; i < HALF; i++) {
-      const double2 v = w.theta2[j + L * i];
-      th[2 * i] = v.x;
-      th[2 * i + 1] = v.y;
-    }
+    estep3_load_cols<L, KPL, false>(w.theta_g, j, th);
     MRLDA_TICK_DEP(1, th[KPL - 1]);
     if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // in flight behind the register batches
     if constexpr (R > 0) {
@@ -249,16 +290,9 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
 #pragma unroll
       for (int q = 0; q < R; q++) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
 #pragma unroll
-      for (int c = 0; c < KPL; c += 4) {
+      for (int c = 0; c < KPL; c++) {
 #pragma unroll
-        for (int q = 0; q < R; q++) {
-          acc[q][0] = fma(th[c], e[q][c], acc[q][0]);
-          acc[q][1] = fma(th[c + 1], e[q][c + 1], acc[q][1]);
-          if (c + 2 < KPL) {
-            acc[q][2] = fma(th[c + 2], e[q][c + 2], acc[q][2]);
-            acc[q][3] = fma(th[c + 3], e[q][c + 3], acc[q][3]);
-          }
-        }
+        for (int q = 0; q < R; q++) acc[q][c & 3] = fma(th[c], e[q][c], acc[q][c & 3]);
       }
 #pragma unroll
       for (int q = 0; q < R; q++) pr[q] = (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
@@ -269,46 +303,26 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
     for (int t = 0; t < NTM; t++) {
       tmem_wait_ld();
       tmem_ld_words<2 * CB>(w.tbase + (uint32_t)(t * TW + 2 * CA), wb);
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      double ac[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int c = 0; c < CA; c += 4) {
-        a0 = fma(th[c], estep3_w2d(wa[2 * c], wa[2 * c + 1]), a0);
-        a1 = fma(th[c + 1], estep3_w2d(wa[2 * c + 2], wa[2 * c + 3]), a1);
-        a2 = fma(th[c + 2], estep3_w2d(wa[2 * c + 4], wa[2 * c + 5]), a2);
-        a3 = fma(th[c + 3], estep3_w2d(wa[2 * c + 6], wa[2 * c + 7]), a3);
-      }
+      for (int c = 0; c < CA; c++) ac[c & 3] = fma(th[c], estep3_w2d(wa[2 * c], wa[2 * c + 1]), ac[c & 3]);
       tmem_wait_ld();
       if (t + 1 < NTM) tmem_ld_words<2 * CA>(w.tbase + (uint32_t)((t + 1) * TW), wa);
 #pragma unroll
-      for (int c = 0; c < CB; c += 2) {
-        if (c & 2) {
-          a2 = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), a2);
-          a3 = fma(th[CA + c + 1], estep3_w2d(wb[2 * c + 2], wb[2 * c + 3]), a3);
-        } else {
-          a0 = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), a0);
-          a1 = fma(th[CA + c + 1], estep3_w2d(wb[2 * c + 2], wb[2 * c + 3]), a1);
-        }
-      }
-      pr[R + t] = (a0 + a1) + (a2 + a3);
+      for (int c = 0; c < CB; c++)
+        ac[c & 3] = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), ac[c & 3]);
+      pr[R + t] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
       if (R + t == N1 - 1 && N1 > R)
         estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
     }
 #pragma unroll
     for (int m = 0; m < NSM; m++) {
-      const double2 *src = w.tile2 + (size_t)m * HALF * 32;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      double ev[KPL];
+      estep3_tile_ld<KPL>(w.tile_w + (size_t)m * 32 * KPL, lane, ev);
+      double ac[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int i = 0; i < HALF; i++) {
-        const double2 v = src[(size_t)i * 32];
-        if (i & 1) {
-          a2 = fma(th[2 * i], v.x, a2);
-          a3 = fma(th[2 * i + 1], v.y, a3);
-        } else {
-          a0 = fma(th[2 * i], v.x, a0);
-          a1 = fma(th[2 * i + 1], v.y, a1);
-        }
-      }
-      pr[R + NTM + m] = (a0 + a1) + (a2 + a3);
+      for (int c = 0; c < KPL; c++) ac[c & 3] = fma(th[c], ev[c], ac[c & 3]);
+      pr[R + NTM + m] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
       if (R + NTM + m == N1 - 1 && N1 > R)
         estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
     }
@@ -339,32 +353,31 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
   }
 #pragma unroll
   for (int m = 0; m < NSM; m++) {
-    const double2 *src = w.tile2 + (size_t)m * HALF * 32;
+    double ev[KPL];
+    estep3_tile_ld<KPL>(w.tile_w + (size_t)m * 32 * KPL, lane, ev);
     const double r = rr[R + NTM + m];
 #pragma unroll
-    for (int i = 0; i < HALF; i++) {
-      const double2 v = src[(size_t)i * 32];
-      s[2 * i] = fma(r, v.x, s[2 * i]);
-      s[2 * i + 1] = fma(r, v.y, s[2 * i + 1]);
-    }
+    for (int c = 0; c < KPL; c++) s[c] = fma(r, ev[c], s[c]);
   }
 }
 
 // The last sweep (generic over the batch count): one fused pass per batch with the likelihood terms
 // (DocumentMapper.java:421) and the statistics scatter (:315-329).
 template <int L, int KPL>
-__device__ __forceinline__ void estep3_last_batch(const EstepArgs &a, const double2 *theta2, const double *cnt_w,
+__device__ __forceinline__ void estep3_last_batch(const EstepArgs &a, const double *theta_g, const double *cnt_w,
                                                   const double (&ev)[KPL], const int slot, const int64_t zrow0,
                                                   const int g, const int j, double (&s)[KPL], double &lik,
                                                   unsigned &badbits) {
-  constexpr int RPB = 32 / L, HALF = KPL / 2;
+  constexpr int RPB = 32 / L, HP = KPL / 2;
+  const double2 *theta2 = reinterpret_cast<const double2 *>(theta_g);
   double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-  for (int i = 0; i < HALF; i++) {
+  for (int i = 0; i < HP; i++) {
     const double2 tv = theta2[j + L * i];
     a0 = fma(tv.x, ev[2 * i], a0);
     a1 = fma(tv.y, ev[2 * i + 1], a1);
   }
+  if constexpr (KPL & 1) a0 = fma(theta_g[2 * L * HP + j], ev[KPL - 1], a0);
   double p = a0 + a1;
 #pragma unroll
   for (int o = 1; o < L; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
@@ -377,7 +390,7 @@ __device__ __forceinline__ void estep3_last_batch(const EstepArgs &a, const doub
   if (r > 0.0) {
     const int term = __ldg(a.term_id + zrow0 + slot * RPB + g);
     if (j == 0) lik = fma(cn, log(p) + __ldg(a.rowmax + term - 1), lik);
-    if (a.learning) estep3_scatter<L, KPL>(a.stats + (size_t)(term - 1) * a.K, theta2, r, ev, j, a.K);
+    if (a.learning) estep3_scatter<L, KPL>(a.stats + (size_t)(term - 1) * a.K, theta_g, r, ev, j, a.K);
   }
 }
 template <int L, int KPL, int R, int NW>
@@ -386,13 +399,13 @@ __device__ __forceinline__ void estep3_sweep_last(const EstepArgs &a, const Este
                                                   double (&s)[KPL], double &lik, unsigned &badbits,
                                                   const int nb, const int64_t zrow0) {
   using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int HALF = S::HALF, T = S::T, TW = S::TW;
+  constexpr int T = S::T, TW = S::TW;
   badbits = 0;
 #pragma unroll
   for (int c = 0; c < KPL; c++) s[c] = 0.0;
 #pragma unroll
   for (int q = 0; q < R; q++)
-    estep3_last_batch<L, KPL>(a, w.theta2, w.cnt_w, e[q], q, zrow0, w.g, w.j, s, lik, badbits);
+    estep3_last_batch<L, KPL>(a, w.theta_g, w.cnt_w, e[q], q, zrow0, w.g, w.j, s, lik, badbits);
 #pragma unroll 1
   for (int t = 0; R + t < nb && t < T; t++) {
     uint32_t w32[TW];
@@ -401,19 +414,13 @@ __device__ __forceinline__ void estep3_sweep_last(const EstepArgs &a, const Este
     double ev[KPL];
 #pragma unroll
     for (int c = 0; c < KPL; c++) ev[c] = estep3_w2d(w32[2 * c], w32[2 * c + 1]);
-    estep3_last_batch<L, KPL>(a, w.theta2, w.cnt_w, ev, R + t, zrow0, w.g, w.j, s, lik, badbits);
+    estep3_last_batch<L, KPL>(a, w.theta_g, w.cnt_w, ev, R + t, zrow0, w.g, w.j, s, lik, badbits);
   }
 #pragma unroll 1
   for (int m = 0; R + T + m < nb; m++) {
-    const double2 *src = w.tile2 + (size_t)m * HALF * 32;
     double ev[KPL];
-#pragma unroll
-    for (int i = 0; i < HALF; i++) {
-      const double2 v = src[(size_t)i * 32];
-      ev[2 * i] = v.x;
-      ev[2 * i + 1] = v.y;
-    }
-    estep3_last_batch<L, KPL>(a, w.theta2, w.cnt_w, ev, R + T + m, zrow0, w.g, w.j, s, lik, badbits);
+    estep3_tile_ld<KPL>(w.tile_w + (size_t)m * 32 * KPL, w.g * L + w.j, ev);
+    estep3_last_batch<L, KPL>(a, w.theta_g, w.cnt_w, ev, R + T + m, zrow0, w.g, w.j, s, lik, badbits);
   }
 }
 
@@ -425,11 +432,17 @@ __device__ __forceinline__ void estep3_sweep_last(const EstepArgs &a, const Este
 template <int L, int KPL>
 __device__ __forceinline__ void estep3_publish_s(const double (&s)[KPL], double *wtot_w, const int lane) {
   static_assert(L == 8, "the row-group reduce-scatter is written for four row groups per warp");
-  constexpr int HALF = KPL / 2, H2 = HALF / 2, LO = HALF - H2;
+  constexpr int HP = KPL / 2, H2 = HP / 2, LO = HP - H2;
   const bool up1 = (lane & 16) != 0, up2 = (lane & 8) != 0;
-  double v[HALF];
+  if constexpr (KPL & 1) {  // the single column of an odd KPL: plain butterfly over the row groups
+    double t = s[KPL - 1];
+    t += __shfl_xor_sync(0xffffffffu, t, 16);
+    t += __shfl_xor_sync(0xffffffffu, t, 8);
+    if (lane < L) wtot_w[2 * L * HP + lane] = t;
+  }
+  double v[HP];
 #pragma unroll
-  for (int m = 0; m < HALF; m++) {
+  for (int m = 0; m < HP; m++) {
     const double send = up1 ? s[2 * m] : s[2 * m + 1];
     const double keep = up1 ? s[2 * m + 1] : s[2 * m];
     v[m] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
@@ -526,7 +539,7 @@ __device__ __forceinline__ void estep3_run_sweeps(const EstepArgs &a, const Este
                                                   double *wtot_w, const int nb, const int64_t zrow0,
                                                   const int lane) {
   using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int HALF = KPL / 2, GT = 32 * G, NA = R + NTM + NSM;
+  constexpr int GT = 32 * G, NA = R + NTM + NSM;
   // n_w of the (batch, row) whose norm this lane completes in the two reduce-scatters: batches j and
   // N1 + j, row g
   constexpr int N1 = Estep3Halves<R, NA>::N1;
@@ -586,7 +599,7 @@ __device__ __forceinline__ void estep3_dispatch(const EstepArgs &a, const Estep3
 template <int L, int KPL, int R, int NW, int G>
 __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int RPB = S::RPB, KS = S::KS, HALF = S::HALF, TW = S::TW, T = S::T, NBMAX = S::NBMAX;
+  constexpr int RPB = S::RPB, KS = S::KS, TW = S::TW, T = S::T, NBMAX = S::NBMAX;
   constexpr int THREADS = S::THREADS;
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x;
@@ -600,8 +613,8 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   Estep3Warp<L, KPL, R, NW> w;
   w.g = lane / L;
   w.j = lane % L;
-  double2 *tile2 = reinterpret_cast<double2 *>(smem + lay.tile) + (size_t)warp * M * HALF * 32 + lane;
-  w.tile2 = tile2;
+  double *tile_w = smem + lay.tile + (size_t)warp * M * 32 * KPL;
+  w.tile_w = tile_w;
   double *cnt_w = smem + lay.cnt + (size_t)warp * (NBMAX * RPB);
   w.cnt_w = cnt_w;
   Estep3Group q;
@@ -614,7 +627,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   q.gt = gw * 32 + lane;
   q.bar_id = 1 + grp;
   q.K = K;
-  w.theta2 = reinterpret_cast<const double2 *>(q.theta_g);
+  w.theta_g = q.theta_g;
   double *wtot_w = q.spart + (size_t)warp * KS;
   double *ssacc_s = smem + lay.ssacc;
   double *red_s = smem + lay.red;  // [warp][4]
@@ -667,14 +680,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
         const bool valid = bi < nb && row < n;
         const int rowc = valid ? row : n - 1;
         double v[KPL];
-        const double2 *src = reinterpret_cast<const double2 *>(
-            a.E + (size_t)(__ldg(a.term_id + b + rowc) - 1) * a.e_stride) + w.j;
-#pragma unroll
-        for (int i = 0; i < HALF; i++) {
-          const double2 t2 = __ldg(src + L * i);
-          v[2 * i] = t2.x;
-          v[2 * i + 1] = t2.y;
-        }
+        estep3_load_cols<L, KPL, true>(a.E + (size_t)(__ldg(a.term_id + b + rowc) - 1) * a.e_stride, w.j, v);
         if (valid && w.j == 0) cnt_w[bi * RPB + w.g] = (double)__ldg(a.count + b + row);
         if (bi < R) {
 #pragma unroll
@@ -688,9 +694,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
           }
           tmem_st_words<TW>(w.tbase + (uint32_t)(bi - R) * TW, w32);
         } else {
-          double2 *dst = tile2 + (size_t)(bi - R - T) * HALF * 32;
-#pragma unroll
-          for (int i = 0; i < HALF; i++) dst[(size_t)i * 32] = make_double2(v[2 * i], v[2 * i + 1]);
+          estep3_tile_st<KPL>(tile_w + (size_t)(bi - R - T) * 32 * KPL, lane, v);
         }
       }
     }
@@ -817,5 +821,7 @@ static cudaError_t variant3_launch(const EstepArgs &args, int grid, int G, int M
 
 extern const Estep3Variant g_estep3_variants_L8[];
 extern const int g_estep3_variants_L8_n;
+extern const Estep3Variant g_estep3_variants_L8o[];
+extern const int g_estep3_variants_L8o_n;
 
 }  // namespace mrlda

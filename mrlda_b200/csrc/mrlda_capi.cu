@@ -549,8 +549,8 @@ static const Estep3Variant *select_variant3(int K) {
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");
   if (fk && (atoi(fk) == 1 || atoi(fk) == 2)) return nullptr;
   const int want_nw = 8;  // 12- and 16-warp CTAs (no register batches) measured 1.5x / 1.8x slower
-  const Estep3Variant *tabs[] = {g_estep3_variants_L8};
-  const int ns[] = {g_estep3_variants_L8_n};
+  const Estep3Variant *tabs[] = {g_estep3_variants_L8, g_estep3_variants_L8o};
+  const int ns[] = {g_estep3_variants_L8_n, g_estep3_variants_L8o_n};
   const Estep3Variant *best = nullptr;
   for (size_t t = 0; t < sizeof(ns) / sizeof(ns[0]); t++)
     for (int i = 0; i < ns[t]; i++) {

@@ -112,4 +112,18 @@ struct TmemVec<4> {
   }
 };
 
+template <>
+struct TmemVec<2> {
+  static __device__ __forceinline__ void ld(uint32_t taddr, uint32_t (&r)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];"
+                 : "=r"(r[0]), "=r"(r[1])
+                 : "r"(taddr));
+  }
+  static __device__ __forceinline__ void st(uint32_t taddr, const uint32_t (&r)[2]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1])
+                 : "memory");
+  }
+};
+
 }  // namespace mrlda
