@@ -275,7 +275,7 @@ estep_kernel(const EstepArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int tid = threadIdx.x, T = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, NW = T >> 5;
-  const int g = lane / L, j = lane % L;
+  const int j = lane % L;
   const int K = a.K;
   const int cap = a.cap_rows;
 
