@@ -1,0 +1,48 @@
+"""The Java side of the boundary ships as source (java/): there is no JDK in this image, so the CPU
+suite checks what it can — the JNI glue compiles against a minimal jni.h, every native method of
+cc.mrlda.b200.MrLdaB200 has its C function, and the glue only calls symbols the ABI header declares."""
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+JAVA = os.path.join(ROOT, "java", "cc", "mrlda", "b200")
+GLUE = os.path.join(ROOT, "java", "jni", "mrlda_b200_jni.c")
+HEADER = os.path.join(ROOT, "include", "mrlda_b200.h")
+
+
+def test_jni_glue_compiles_against_stub_jni_h():
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Wextra", "-Werror",
+                        "-I", os.path.join(ROOT, "tests", "jni_stub"), "-I", os.path.join(ROOT, "include"), GLUE],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_every_native_method_has_a_jni_function():
+    src = open(os.path.join(JAVA, "MrLdaB200.java")).read()
+    natives = re.findall(r"\bnative\s+[\w\[\]]+\s+(\w+)\s*\(", src)
+    assert len(natives) >= 14
+    glue = open(GLUE).read()
+    defined = set(re.findall(r"Java_cc_mrlda_b200_MrLdaB200_(\w+)\s*\(", glue))
+    assert set(natives) == defined, (sorted(set(natives) - defined), sorted(defined - set(natives)))
+
+
+def test_glue_calls_only_declared_abi_symbols():
+    header = open(HEADER).read()
+    declared = set(re.findall(r"\b(mrlda_\w+)\s*\(", header))
+    used = set(re.findall(r"\b(mrlda_\w+)\s*\(", open(GLUE).read()))
+    assert used and used <= declared, sorted(used - declared)
+
+
+def test_helper_classes_and_patch_are_present():
+    for name in ("MrLdaB200.java", "CsrCorpus.java", "BetaFile.java", "GammaDir.java"):
+        text = open(os.path.join(JAVA, name)).read()
+        assert "package cc.mrlda.b200;" in text and text.count("{") == text.count("}")
+    patch = open(os.path.join(ROOT, "java", "VariationalInference.patch")).read()
+    assert patch.startswith("--- a/src/main/java/cc/mrlda/VariationalInference.java")
+    # hunk headers are consistent with their bodies
+    for m in re.finditer(r"^@@ -(\d+),(\d+) \+(\d+),(\d+) @@.*\n((?:[ +\-].*\n|\n)*)", patch, re.M):
+        body = m.group(5).splitlines()
+        old = sum(1 for l in body if l[:1] in (" ", "-") or l == "")
+        new = sum(1 for l in body if l[:1] in (" ", "+") or l == "")
+        assert (old, new) == (int(m.group(2)), int(m.group(4))), m.group(0)[:80]
