@@ -747,8 +747,7 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
         estep2_sweep<NW, CPW, RREG, WPS, CL, true>(a, e, es, part, cnt_s, r_s, meta_s + 1, theta_w, s, lik,
                                           badbits, b, n, nslots, cap_rows, warp, lane, tm, tbase, rt, crank, tail_s);
       MRLDA_TICK_DEP(6, s[CPW - 1]);
-      // (4) S_c to the owner lane: transpose through the spare shared-memory slot when the
-      // document leaves it free, else reduce-scatter in registers
+      // (4) S_c to the owner lane: reduce-scatter in registers (shuffles)
       double S_c;
       {
         int base = 0, cnt = CPW;
@@ -896,8 +895,6 @@ extern const Estep2Variant g_estep2_variants_W4[];
 extern const int g_estep2_variants_W4_n;
 extern const Estep2Variant g_estep2_variants_W8[];
 extern const int g_estep2_variants_W8_n;
-extern const Estep2Variant g_estep2_variants_W16[];
-extern const int g_estep2_variants_W16_n;
 extern const Estep2Variant g_estep2_variants_C2[];
 extern const int g_estep2_variants_C2_n;
 extern const Estep2Variant g_estep2_variants_C4[];

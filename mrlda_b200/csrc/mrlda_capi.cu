@@ -28,9 +28,6 @@
 
 using namespace mrlda;
 
-#ifndef MRLDA_DEFAULT_WPS
-#define MRLDA_DEFAULT_WPS 8
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // small device kernels
@@ -508,31 +505,28 @@ static const EstepVariant *select_variant(int K) {
 
 static const Estep2Variant *select_variant2(int K) {
   const Estep2Variant *tabs[] = {g_estep2_variants_W1, g_estep2_variants_W2, g_estep2_variants_W4,
-                                 g_estep2_variants_W8, g_estep2_variants_W16, g_estep2_variants_C2,
-                                 g_estep2_variants_C4};
+                                 g_estep2_variants_W8, g_estep2_variants_C2, g_estep2_variants_C4};
   const int ns[] = {g_estep2_variants_W1_n, g_estep2_variants_W2_n, g_estep2_variants_W4_n,
-                    g_estep2_variants_W8_n, g_estep2_variants_W16_n, g_estep2_variants_C2_n,
-                    g_estep2_variants_C4_n};
+                    g_estep2_variants_W8_n, g_estep2_variants_C2_n, g_estep2_variants_C4_n};
   const char *force = getenv("MRLDA_ESTEP2_VARIANT");  // "NW,CPW[,RREG]" — profiling aid
   int fw = 0, fc = 0, fr = 0;
   if (force && sscanf(force, "%d,%d,%d", &fw, &fc, &fr) < 2) fw = fc = fr = 0;
-  const char *ew = getenv("MRLDA_ESTEP2_WPS");  // warps per SM class: 8 or 16
-  const int wps = ew ? atoi(ew) : MRLDA_DEFAULT_WPS;
-  const int max_cpw = wps == 16 ? 16 : 26;
+  const int wps = 8;       // warps per SM: the 16-warp class (128 registers) measured slower and is gone
+  const int max_cpw = 26;
   // fewest warps per CTA whose column slice stays <= max_cpw doubles, then the narrowest slice;
   // beyond 8 warps x 32 columns the topic split continues across a cluster of 2 or 4 CTAs
   const Estep2Variant *best = nullptr;
-  for (int t = 0; t < 7; t++) {
+  for (int t = 0; t < 6; t++) {
     for (int i = 0; i < ns[t]; i++) {
       const Estep2Variant *v = &tabs[t][i];
       if (v->CL * v->NW * v->CPW < K) continue;
       if (fw) {
         if (v->CL == 1 && v->NW == fw && v->CPW == fc &&
-            (fr ? v->RREG == fr : v->RREG == estep2_rreg(v->CPW, v->WPS)) && (!ew || v->WPS == wps))
+            (fr ? v->RREG == fr : v->RREG == estep2_rreg(v->CPW, v->WPS)) && v->WPS == wps)
           return v;
         continue;
       }
-      if (v->WPS != (t >= 5 ? 8 : wps) || v->RREG != estep2_rreg(v->CPW, v->WPS)) continue;
+      if (v->WPS != wps || v->RREG != estep2_rreg(v->CPW, v->WPS)) continue;
       if (!best || v->CPW < best->CPW) best = v;
     }
     if (best) {
