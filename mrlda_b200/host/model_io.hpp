@@ -6,6 +6,7 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -51,11 +52,15 @@ inline std::vector<std::string> input_files(const std::string &path) {
 }
 
 // SequenceFile<IntWritable, cc.mrlda.Document> -> CSR.  Entry order within a document is the
-// writer's HMapII iteration order (arbitrary); it is kept as found.
-inline Corpus read_corpus(const std::string &path, int n_topics, int n_terms) {
+// writer's HMapII iteration order (arbitrary); it is kept as found.  Only the documents with
+// global index in [first, last) are kept (the others are skipped without being parsed).
+inline Corpus read_corpus(const std::string &path, int n_topics, int n_terms, int64_t first = 0,
+                          int64_t last = INT64_MAX) {
   Corpus c;
   bool all_gamma = true;
+  int64_t index = 0;
   for (const std::string &file : input_files(path)) {
+    if (index >= last) break;
     SeqReader r(file);
     if (r.key_class != kIntWritable || r.value_class != kDocument)
       throw std::invalid_argument(file + ": expected <" + kIntWritable + ", " + kDocument + ">, found <" +
@@ -63,7 +68,8 @@ inline Corpus read_corpus(const std::string &path, int n_topics, int n_terms) {
     const uint8_t *k, *v;
     size_t kl, vl;
     Document doc;
-    while (r.next(k, kl, v, vl)) {
+    while (index < last && r.next(k, kl, v, vl)) {
+      if (index++ < first) continue;
       ByteReader kr(k, kl), vr(v, vl);
       c.doc_id.push_back(kr.i32());
       doc.read(vr);
@@ -84,6 +90,46 @@ inline Corpus read_corpus(const std::string &path, int n_topics, int n_terms) {
   }
   if (!all_gamma) c.gamma.clear();
   return c;
+}
+
+// The input split of one rank (the map phase's input splits): a first streaming pass reads only
+// the entry count at the head of every Document value and cuts the document range into `world`
+// contiguous pieces balanced by entries, as corpus.shard_bounds does; the second pass parses this
+// rank's piece alone, so no rank ever holds more than its own shard.  first_doc receives the
+// global index of the shard's first document.
+inline Corpus read_corpus_shard(const std::string &path, int n_topics, int n_terms, int rank, int world,
+                                int64_t *first_doc = nullptr, int64_t *total_docs = nullptr) {
+  if (world <= 1) {
+    Corpus c = read_corpus(path, n_topics, n_terms);
+    if (first_doc) *first_doc = 0;
+    if (total_docs) *total_docs = c.n_docs();
+    return c;
+  }
+  std::vector<int64_t> rp{0};
+  for (const std::string &file : input_files(path)) {
+    SeqReader r(file);
+    if (r.key_class != kIntWritable || r.value_class != kDocument)
+      throw std::invalid_argument(file + ": expected <" + kIntWritable + ", " + kDocument + ">, found <" +
+                                  r.key_class + ", " + r.value_class + ">");
+    const uint8_t *k, *v;
+    size_t kl, vl;
+    while (r.next(k, kl, v, vl)) {
+      ByteReader vr(v, vl);
+      const int32_t n = vr.i32();
+      rp.push_back(rp.back() + (n > 0 ? n : 0));
+    }
+  }
+  const int64_t D = (int64_t)rp.size() - 1, Z = rp.back();
+  auto bound = [&](int r) -> int64_t {
+    if (r <= 0) return 0;
+    if (r >= world) return D;
+    return std::lower_bound(rp.begin(), rp.end(), Z * r / world) - rp.begin();
+  };
+  const int64_t lo = std::min(bound(rank), D);
+  const int64_t hi = std::min(std::max(bound(rank + 1), lo), D);
+  if (first_doc) *first_doc = lo;
+  if (total_docs) *total_docs = D;
+  return read_corpus(path, n_topics, n_terms, lo, hi);
 }
 
 // exportAlpha (VariationalInference.java:549-558)

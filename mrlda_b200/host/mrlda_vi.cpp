@@ -269,28 +269,18 @@ int main(int argc, char **argv) {
       if (mrlda_comm_init(ctx, id) != MRLDA_OK) die(ctx, "mrlda_comm_init");
     }
 
-    // the input split of this rank: contiguous documents balanced by nnz
-    Corpus all = read_corpus(input_dir, K, V);
-    int64_t lo = 0, hi = all.n_docs();
-    if (o.world > 1) {
-      const int64_t Z = all.row_ptr.back();
-      auto bound = [&](int r) -> int64_t {
-        if (r <= 0) return 0;
-        if (r >= o.world) return all.n_docs();
-        return std::lower_bound(all.row_ptr.begin(), all.row_ptr.end(), Z * r / o.world) -
-               all.row_ptr.begin();
-      };
-      lo = std::min(bound(o.rank), all.n_docs());
-      hi = std::min(std::max(bound(o.rank + 1), lo), all.n_docs());
-    }
-    std::vector<int64_t> rp((size_t)(hi - lo + 1));
-    for (int64_t d = lo; d <= hi; d++) rp[(size_t)(d - lo)] = all.row_ptr[d] - all.row_ptr[lo];
-    const int64_t z0 = all.row_ptr[lo];
+    // the input split of this rank: contiguous documents balanced by nnz; a rank reads (and keeps)
+    // only its own shard
+    int64_t first_doc = 0, total_docs = 0;
+    Corpus all = read_corpus_shard(input_dir, K, V, o.rank, o.world, &first_doc, &total_docs);
+    const int64_t lo = 0, hi = all.n_docs();
     const bool stored_gamma = !all.gamma.empty();
-    if (mrlda_set_corpus_csr(ctx, hi - lo, rp.data(), all.term_id.data() + z0, all.count.data() + z0,
-                             all.doc_id.data() + lo,
-                             stored_gamma ? all.gamma.data() + (size_t)lo * K : nullptr) != MRLDA_OK)
+    if (mrlda_set_corpus_csr(ctx, hi, all.row_ptr.data(), all.term_id.data(), all.count.data(),
+                             all.doc_id.data(), stored_gamma ? all.gamma.data() : nullptr) != MRLDA_OK)
       die(ctx, "mrlda_set_corpus_csr");
+    if (o.world > 1)
+      info(" - input split of rank " + std::to_string(o.rank) + ": documents [" + std::to_string(first_doc) +
+           ", " + std::to_string(first_doc + hi) + ") of " + std::to_string(total_docs));
 
     double last_ll = 0;
     int iteration = o.snapshot;

@@ -1,5 +1,6 @@
 // seqfile.hpp — the wire formats either side of the hot path:
-// Hadoop SequenceFile (version 6, uncompressed records) and the Writables Mr.LDA stores in it.
+// Hadoop SequenceFile (versions 5 and 6; written uncompressed, read uncompressed, record- or
+// block-compressed with the zlib / gzip codecs) and the Writables Mr.LDA stores in it.
 //
 //   cc.mrlda.Document                      Document.java:147-172 (readFields), :241-263 (write)
 //   alpha files  <IntWritable, DoubleWritable>   VariationalInference.java:521-558
@@ -16,10 +17,13 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
+
+#include <zlib.h>
 
 namespace mrlda_host {
 
@@ -230,73 +234,204 @@ class SeqWriter {
   int64_t pos_ = 0, last_sync_ = 0;
 };
 
+// Streaming reader: the file is read through a bounded buffer, one record (or one compressed block)
+// at a time, so memory does not grow with the file.  Handles what SequenceFile.Reader handles for
+// the codecs that need no native Hadoop library: uncompressed records, record-compressed values
+// and block-compressed files with org.apache.hadoop.io.compress.DefaultCodec (zlib streams) or
+// GzipCodec (the reference opens its inputs with a plain SequenceFile.Reader,
+// VariationalInference.java:282,288 and DocumentMapper.java:475-536, so whatever codec the cluster
+// wrote is accepted there).  Other codecs (Snappy, LZ4, BZip2) are refused by name.
 class SeqReader {
  public:
-  explicit SeqReader(const std::string &path) {
-    FILE *f = fopen(path.c_str(), "rb");
-    if (!f) throw std::runtime_error("cannot open " + path);
-    fseek(f, 0, SEEK_END);
-    long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    data_.resize((size_t)n);
-    if (n && fread(data_.data(), 1, (size_t)n, f) != (size_t)n) {
-      fclose(f);
-      throw std::runtime_error("short read " + path);
-    }
-    fclose(f);
-    ByteReader r(data_.data(), data_.size());
-    r.need(4);
-    if (memcmp(r.p, "SEQ", 3) != 0) throw std::runtime_error(path + ": not a SequenceFile");
-    r.p += 3;
-    int ver = r.u8();
-    if (ver < 5 || ver > 6) throw std::runtime_error(path + ": unsupported SequenceFile version");
-    key_class = r.text();
-    value_class = r.text();
-    bool comp = r.u8() != 0, block = r.u8() != 0;
-    if (comp || block)
-      throw std::runtime_error(path + ": compressed SequenceFiles are not supported (ParseCorpus "
-                                      "writes uncompressed records, ParseCorpus.java:680)");
-    if (ver >= 6) {  // the metadata block came with version 6 (VERSION_WITH_METADATA)
-      int32_t meta = r.i32();
-      for (int32_t i = 0; i < meta; i++) {
-        r.text();
-        r.text();
+  explicit SeqReader(const std::string &path) : path_(path), f_(fopen(path.c_str(), "rb")) {
+    if (!f_) throw std::runtime_error("cannot open " + path);
+    try {
+      uint8_t magic[4];
+      read_exact(magic, 4, "header");
+      if (memcmp(magic, "SEQ", 3) != 0) throw std::runtime_error(path + ": not a SequenceFile");
+      const int ver = magic[3];
+      if (ver < 5 || ver > 6) throw std::runtime_error(path + ": unsupported SequenceFile version");
+      key_class = read_text();
+      value_class = read_text();
+      uint8_t flags[2];
+      read_exact(flags, 2, "header");
+      compressed_ = flags[0] != 0;
+      block_ = flags[1] != 0;
+      if (compressed_) {
+        codec = read_text();
+        if (codec != "org.apache.hadoop.io.compress.DefaultCodec" &&
+            codec != "org.apache.hadoop.io.compress.GzipCodec")
+          throw std::runtime_error(path + ": SequenceFile codec " + codec +
+                                   " is not supported (DefaultCodec and GzipCodec are)");
       }
+      if (ver >= 6) {  // the metadata block came with version 6 (VERSION_WITH_METADATA)
+        const int32_t meta = read_i32("header");
+        for (int32_t i = 0; i < meta; i++) {
+          read_text();
+          read_text();
+        }
+      }
+      read_exact(sync_, 16, "header");
+    } catch (...) {
+      fclose(f_);
+      f_ = nullptr;
+      throw;
     }
-    r.need(16);
-    memcpy(sync_, r.p, 16);
-    r.p += 16;
-    off_ = (size_t)(r.p - data_.data());
   }
-  // next record; key/value point into the file buffer
+  ~SeqReader() {
+    if (f_) fclose(f_);
+  }
+  SeqReader(const SeqReader &) = delete;
+  SeqReader &operator=(const SeqReader &) = delete;
+
+  // next record; key/value stay valid until the following call
   bool next(const uint8_t *&key, size_t &klen, const uint8_t *&val, size_t &vlen) {
+    if (block_) return next_in_block(key, klen, val, vlen);
     for (;;) {
-      if (off_ >= data_.size()) return false;
-      ByteReader r(data_.data() + off_, data_.size() - off_);
-      int32_t rec = r.i32();
+      uint8_t h[4];
+      const size_t got = fread(h, 1, 4, f_);
+      if (got == 0) return false;
+      if (got != 4) throw std::runtime_error("unexpected end of data");
+      const int32_t rec = be32(h);
       if (rec == -1) {  // sync escape
-        r.need(16);
-        if (memcmp(r.p, sync_, 16) != 0) throw std::runtime_error("corrupt sync marker");
-        off_ += 20;
+        check_sync();
         continue;
       }
-      int32_t kl = r.i32();
+      const int32_t kl = read_i32("record header");
       if (rec < 0 || kl < 0 || kl > rec) throw std::runtime_error("corrupt record header");
-      r.need((size_t)rec);
-      key = r.p;
+      rec_.resize((size_t)rec);
+      read_exact(rec_.data(), (size_t)rec, "record");
+      key = rec_.data();
       klen = (size_t)kl;
-      val = r.p + kl;
-      vlen = (size_t)(rec - kl);
-      off_ += 8 + (size_t)rec;
+      if (compressed_) {  // the value alone is a codec stream
+        inflate_into(rec_.data() + kl, (size_t)(rec - kl), val_);
+        val = val_.data();
+        vlen = val_.size();
+      } else {
+        val = rec_.data() + kl;
+        vlen = (size_t)(rec - kl);
+      }
       return true;
     }
   }
-  std::string key_class, value_class;
+  std::string key_class, value_class, codec;
+  bool compressed() const { return compressed_; }
+  bool block_compressed() const { return block_; }
 
  private:
-  std::vector<uint8_t> data_;
+  static int32_t be32(const uint8_t *h) {
+    return (int32_t)(((uint32_t)h[0] << 24) | ((uint32_t)h[1] << 16) | ((uint32_t)h[2] << 8) | h[3]);
+  }
+  void read_exact(uint8_t *dst, size_t n, const char *what) {
+    if (n && fread(dst, 1, n, f_) != n)
+      throw std::runtime_error(std::string("unexpected end of data (") + what + ")");
+  }
+  int32_t read_i32(const char *what) {
+    uint8_t h[4];
+    read_exact(h, 4, what);
+    return be32(h);
+  }
+  int64_t read_vlong() {  // WritableUtils.readVLong from the stream
+    uint8_t b[9];
+    read_exact(b, 1, "vint");
+    const int8_t first = (int8_t)b[0];
+    const int len = first >= -112 ? 1 : (first < -120 ? -119 - first : -111 - first);
+    read_exact(b + 1, (size_t)(len - 1), "vint");
+    ByteReader r(b, (size_t)len);
+    return r.vlong();
+  }
+  std::string read_text() {
+    const int64_t n = read_vlong();
+    if (n < 0 || n > (1 << 20)) throw std::runtime_error("corrupt string length");
+    std::string s((size_t)n, '\0');
+    read_exact(reinterpret_cast<uint8_t *>(&s[0]), (size_t)n, "string");
+    return s;
+  }
+  void check_sync() {
+    uint8_t m[16];
+    read_exact(m, 16, "sync marker");
+    if (memcmp(m, sync_, 16) != 0) throw std::runtime_error("corrupt sync marker");
+  }
+  // zlib or gzip stream -> out (the 32 added to the window bits selects the format from the header)
+  void inflate_into(const uint8_t *src, size_t n, std::vector<uint8_t> &out) {
+    z_stream z;
+    memset(&z, 0, sizeof z);
+    if (inflateInit2(&z, 15 + 32) != Z_OK) throw std::runtime_error("inflateInit2 failed");
+    out.resize(std::max<size_t>(out.capacity(), std::max<size_t>(4 * n, 256)));
+    z.next_in = const_cast<Bytef *>(src);
+    z.avail_in = (uInt)n;
+    size_t produced = 0;
+    for (;;) {
+      z.next_out = out.data() + produced;
+      z.avail_out = (uInt)(out.size() - produced);
+      const int rc = inflate(&z, Z_NO_FLUSH);
+      produced = out.size() - z.avail_out;
+      if (rc == Z_STREAM_END) break;
+      if (rc != Z_OK && rc != Z_BUF_ERROR) {
+        inflateEnd(&z);
+        throw std::runtime_error(path_ + ": corrupt compressed data");
+      }
+      if (z.avail_out == 0) {
+        out.resize(out.size() * 2);
+      } else if (z.avail_in == 0) {
+        inflateEnd(&z);
+        throw std::runtime_error(path_ + ": truncated compressed data");
+      }
+    }
+    inflateEnd(&z);
+    out.resize(produced);
+  }
+  void read_block_buffer(std::vector<uint8_t> &out) {
+    const int64_t n = read_vlong();
+    if (n < 0 || n > ((int64_t)1 << 31)) throw std::runtime_error("corrupt block buffer length");
+    rec_.resize((size_t)n);
+    read_exact(rec_.data(), (size_t)n, "block buffer");
+    inflate_into(rec_.data(), (size_t)n, out);
+  }
+  // Block-compressed files (SequenceFile.BlockCompressWriter): sync escape, record count, then the
+  // key lengths, keys, value lengths and values of the block as four codec streams.
+  bool next_in_block(const uint8_t *&key, size_t &klen, const uint8_t *&val, size_t &vlen) {
+    while (left_ == 0) {
+      uint8_t h[4];
+      const size_t got = fread(h, 1, 4, f_);
+      if (got == 0) return false;
+      if (got != 4) throw std::runtime_error("unexpected end of data");
+      if (be32(h) != -1) throw std::runtime_error("corrupt block header (no sync escape)");
+      check_sync();
+      const int64_t n = read_vlong();
+      if (n < 0) throw std::runtime_error("corrupt block record count");
+      read_block_buffer(klens_);
+      read_block_buffer(keys_);
+      read_block_buffer(vlens_);
+      read_block_buffer(vals_);
+      left_ = n;
+      kl_off_ = k_off_ = vl_off_ = v_off_ = 0;
+    }
+    ByteReader kr(klens_.data() + kl_off_, klens_.size() - kl_off_);
+    ByteReader vr(vlens_.data() + vl_off_, vlens_.size() - vl_off_);
+    const int64_t kl = kr.vlong(), vl = vr.vlong();
+    kl_off_ = (size_t)(kr.p - klens_.data());
+    vl_off_ = (size_t)(vr.p - vlens_.data());
+    if (kl < 0 || vl < 0 || k_off_ + (size_t)kl > keys_.size() || v_off_ + (size_t)vl > vals_.size())
+      throw std::runtime_error("corrupt block (lengths exceed the data)");
+    key = keys_.data() + k_off_;
+    klen = (size_t)kl;
+    val = vals_.data() + v_off_;
+    vlen = (size_t)vl;
+    k_off_ += (size_t)kl;
+    v_off_ += (size_t)vl;
+    left_--;
+    return true;
+  }
+
+  std::string path_;
+  FILE *f_;
+  bool compressed_ = false, block_ = false;
   uint8_t sync_[16];
-  size_t off_ = 0;
+  std::vector<uint8_t> rec_, val_;
+  std::vector<uint8_t> klens_, keys_, vlens_, vals_;
+  int64_t left_ = 0;
+  size_t kl_off_ = 0, k_off_ = 0, vl_off_ = 0, v_off_ = 0;
 };
 
 }  // namespace mrlda_host

@@ -66,6 +66,18 @@ mrlda_io_corpus *mrlda_io_read_corpus(const char *path, int32_t k, int32_t v) {
     return nullptr;
   }
 }
+// the input split of one rank (read_corpus_shard): first_doc receives the shard's first global index
+mrlda_io_corpus *mrlda_io_read_corpus_shard(const char *path, int32_t k, int32_t v, int32_t rank,
+                                            int32_t world, int64_t *first_doc, int64_t *total_docs) {
+  try {
+    auto *h = new mrlda_io_corpus();
+    h->c = read_corpus_shard(path, k, v, rank, world, first_doc, total_docs);
+    return h;
+  } catch (const std::exception &e) {
+    g_err = e.what();
+    return nullptr;
+  }
+}
 int64_t mrlda_io_corpus_docs(const mrlda_io_corpus *h) { return h->c.n_docs(); }
 int64_t mrlda_io_corpus_nnz(const mrlda_io_corpus *h) { return (int64_t)h->c.term_id.size(); }
 int mrlda_io_corpus_has_gamma(const mrlda_io_corpus *h) { return h->c.gamma.empty() ? 0 : 1; }

@@ -26,6 +26,9 @@ def load():
         L.mrlda_io_write_corpus.argtypes = [C.c_char_p, C.c_int64, _lp, _ip, _ip, _ip, _dp, C.c_int32]
         L.mrlda_io_read_corpus.restype = C.c_void_p
         L.mrlda_io_read_corpus.argtypes = [C.c_char_p, C.c_int32, C.c_int32]
+        L.mrlda_io_read_corpus_shard.restype = C.c_void_p
+        L.mrlda_io_read_corpus_shard.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                                 C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         for f in ("mrlda_io_corpus_docs", "mrlda_io_corpus_nnz"):
             getattr(L, f).restype = C.c_int64
             getattr(L, f).argtypes = [C.c_void_p]
@@ -95,10 +98,16 @@ def write_corpus(path, row_ptr, term_id, count, doc_id=None, gamma=None, n_topic
                                      g.ctypes.data_as(_dp) if g is not None else None, int(n_topics)))
 
 
-def read_corpus(path, n_topics, n_terms):
-    """Returns dict(row_ptr, term_id, count, doc_id, gamma or None)."""
+def read_corpus(path, n_topics, n_terms, rank=0, world=1):
+    """Returns dict(row_ptr, term_id, count, doc_id, gamma or None); with world > 1 the input split of
+    `rank` alone (contiguous documents balanced by entries), plus first_doc / total_docs."""
     L = load()
-    h = L.mrlda_io_read_corpus(os.fsencode(path), n_topics, n_terms)
+    first, total = C.c_int64(0), C.c_int64(0)
+    if world > 1:
+        h = L.mrlda_io_read_corpus_shard(os.fsencode(path), n_topics, n_terms, rank, world,
+                                         C.byref(first), C.byref(total))
+    else:
+        h = L.mrlda_io_read_corpus(os.fsencode(path), n_topics, n_terms)
     if not h:
         raise SeqFileError(L.mrlda_io_last_error().decode())
     try:
@@ -112,7 +121,10 @@ def read_corpus(path, n_topics, n_terms):
                                did.ctypes.data_as(_ip), g.ctypes.data_as(_dp) if has_g else None)
     finally:
         L.mrlda_io_corpus_free(h)
-    return dict(row_ptr=rp, term_id=t[:Z], count=c[:Z], doc_id=did[:D], gamma=g)
+    out = dict(row_ptr=rp, term_id=t[:Z], count=c[:Z], doc_id=did[:D], gamma=g)
+    if world > 1:
+        out.update(first_doc=first.value, total_docs=total.value)
+    return out
 
 
 def write_alpha(path, alpha):

@@ -9,9 +9,13 @@ mrlda_b200/host/ from the outside:
   * WritableUtils vint, IntWritable, DoubleWritable, cc.mrlda.Document (Document.java:241-263),
     PairOfIntFloat, HMapIDW — all big-endian.
 """
+import gzip
 import struct
+import zlib
 
 SYNC_ESCAPE = -1
+DEFAULT_CODEC = "org.apache.hadoop.io.compress.DefaultCodec"
+GZIP_CODEC = "org.apache.hadoop.io.compress.GzipCodec"
 
 
 def write_vint(i):
@@ -99,6 +103,34 @@ def write_file(path, key_class, value_class, records, sync=bytes(range(16)), syn
         if sync_every and i and i % sync_every == 0:
             out += struct.pack(">i", SYNC_ESCAPE) + sync
         out += struct.pack(">ii", len(k) + len(v), len(k)) + k + v
+    open(path, "wb").write(out)
+
+
+def _deflate(data, codec):
+    return gzip.compress(data) if codec == GZIP_CODEC else zlib.compress(data)
+
+
+def write_compressed_file(path, key_class, value_class, records, block, codec=DEFAULT_CODEC,
+                          sync=bytes(range(16)), per_block=3, sync_every=None):
+    """SequenceFile.RecordCompressWriter (block=False: every value is one codec stream, keys stay
+    plain) or SequenceFile.BlockCompressWriter (block=True: sync escape, vint record count, then key
+    lengths / keys / value lengths / values, each a vint byte count + one codec stream)."""
+    out = (b"SEQ\x06" + text(key_class) + text(value_class) + b"\x01" + (b"\x01" if block else b"\x00") +
+           text(codec) + struct.pack(">i", 0) + sync)
+    if not block:
+        for i, (k, v) in enumerate(records):
+            if sync_every and i and i % sync_every == 0:
+                out += struct.pack(">i", SYNC_ESCAPE) + sync
+            cv = _deflate(v, codec)
+            out += struct.pack(">ii", len(k) + len(cv), len(k)) + k + cv
+    else:
+        for lo in range(0, len(records), per_block):
+            chunk = records[lo:lo + per_block]
+            out += struct.pack(">i", SYNC_ESCAPE) + sync + write_vint(len(chunk))
+            for buf in (b"".join(write_vint(len(k)) for k, _ in chunk), b"".join(k for k, _ in chunk),
+                        b"".join(write_vint(len(v)) for _, v in chunk), b"".join(v for _, v in chunk)):
+                c = _deflate(buf, codec)
+                out += write_vint(len(c)) + c
     open(path, "wb").write(out)
 
 

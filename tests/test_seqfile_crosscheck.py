@@ -89,6 +89,87 @@ def test_corpus_written_by_python_is_read_by_cpp(tmp_path_factory, docs, K, sync
         assert got["gamma"] is None
 
 
+@settings(max_examples=25, deadline=None)
+@given(docs_strategy, st.integers(min_value=0, max_value=3), st.booleans(),
+       st.sampled_from([pyseq.DEFAULT_CODEC, pyseq.GZIP_CODEC]), st.sampled_from([1, 3, 1000]))
+def test_compressed_corpus_is_read_by_cpp(tmp_path_factory, docs, K, block, codec, per_block):
+    """Record- and block-compressed SequenceFiles (zlib / gzip codec streams), as SequenceFile.Reader
+    accepts them for the reference (VariationalInference.java:282, DocumentMapper.java:475-536)."""
+    path = str(tmp_path_factory.mktemp("z") / "part-00000")
+    rng = np.random.default_rng(len(docs) + 5)
+    gamma = rng.gamma(1.0, size=(len(docs), K)) if K else None
+    records = [(struct.pack(">i", d), pyseq.document_bytes(c, gamma[i] if K else None))
+               for i, (d, c) in enumerate(docs)]
+    pyseq.write_compressed_file(path, INT, DOC, records, block, codec=codec, per_block=per_block,
+                                sync=bytes(rng.integers(0, 256, 16, dtype=np.uint8)), sync_every=2)
+    got = seqfile.read_corpus(path, max(K, 1), 500)
+    assert np.array_equal(got["doc_id"], [d for d, _ in docs])
+    assert np.array_equal(np.diff(got["row_ptr"]), [len(c) for _, c in docs])
+    for i, (_, c) in enumerate(docs):
+        lo, hi = got["row_ptr"][i], got["row_ptr"][i + 1]
+        assert dict(zip(got["term_id"][lo:hi].tolist(), got["count"][lo:hi].tolist())) == c
+    if K:
+        assert np.array_equal(got["gamma"], gamma)
+
+
+def test_input_splits_cover_the_corpus(tmp_path):
+    """mrlda-vi ranks read only their own split (read_corpus_shard): the splits are contiguous, balanced
+    by entries like corpus.shard_bounds, and together they are the corpus; part files are read in
+    name order (one of them block-compressed)."""
+    from mrlda_b200 import corpus
+    rng = np.random.default_rng(11)
+    lens = rng.integers(0, 40, 300)
+    docs = [(1000 + i, {int(t): int(rng.integers(1, 5)) for t in rng.choice(400, n, replace=False) + 1})
+            for i, n in enumerate(lens)]
+    recs = [(struct.pack(">i", d), pyseq.document_bytes(c, None)) for d, c in docs]
+    d = tmp_path / "in"
+    d.mkdir()
+    pyseq.write_file(str(d / "part-00000"), INT, DOC, recs[:120], sync_every=7)
+    pyseq.write_compressed_file(str(d / "part-00001"), INT, DOC, recs[120:], True, per_block=16)
+    (d / "_SUCCESS").write_bytes(b"")
+    whole = seqfile.read_corpus(str(d), 1, 500)
+    assert whole["doc_id"].tolist() == [i for i, _ in docs]
+    for world in (2, 3, 8):
+        bounds = corpus.shard_bounds(whole["row_ptr"], world)
+        ids, nnz = [], 0
+        for rank in range(world):
+            part = seqfile.read_corpus(str(d), 1, 500, rank=rank, world=world)
+            assert part["total_docs"] == 300 and part["first_doc"] == bounds[rank]
+            assert len(part["doc_id"]) == bounds[rank + 1] - bounds[rank]
+            lo = whole["row_ptr"][bounds[rank]]
+            assert np.array_equal(part["term_id"], whole["term_id"][lo:lo + len(part["term_id"])])
+            assert np.array_equal(part["count"], whole["count"][lo:lo + len(part["count"])])
+            ids += part["doc_id"].tolist()
+            nnz += len(part["term_id"])
+        assert ids == whole["doc_id"].tolist() and nnz == len(whole["term_id"])
+
+
+def test_compressed_model_files_and_unknown_codecs(tmp_path):
+    """alpha files through both compressed layouts; a codec that needs Hadoop's native library is
+    refused by name; damaged codec streams raise."""
+    alpha = np.array([0.5, 1.25, 3.0])
+    recs = [(struct.pack(">i", i + 1), struct.pack(">d", a)) for i, a in enumerate(alpha)]
+    for block in (False, True):
+        p = str(tmp_path / f"alpha-{int(block)}")
+        pyseq.write_compressed_file(p, INT, DBL, recs, block)
+        assert np.array_equal(seqfile.read_alpha(p, 3), alpha)
+    p = str(tmp_path / "snappy")
+    pyseq.write_compressed_file(p, INT, DBL, recs, False, codec="org.apache.hadoop.io.compress.SnappyCodec")
+    with pytest.raises(seqfile.SeqFileError, match="SnappyCodec"):
+        seqfile.read_alpha(p, 3)
+    p = str(tmp_path / "damaged")
+    pyseq.write_compressed_file(p, INT, DBL, recs, True)
+    raw = bytearray(open(p, "rb").read())
+    raw[-6] ^= 0xFF
+    open(p, "wb").write(bytes(raw))
+    with pytest.raises(seqfile.SeqFileError):
+        seqfile.read_alpha(p, 3)
+    raw = open(p, "rb").read()
+    open(p, "wb").write(raw[:-9])  # truncated block
+    with pytest.raises(seqfile.SeqFileError):
+        seqfile.read_alpha(p, 3)
+
+
 def test_alpha_and_beta_files_cross_check(tmp_path):
     rng = np.random.default_rng(3)
     K, V = 7, 23
