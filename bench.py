@@ -76,8 +76,8 @@ class ClockSampler:
 
 def measured_traffic(workload, n_gpus):
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/r1_traffic.json); None when no capture exists for this workload / GPU count."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    (profiles/r2_traffic.json: the sum over the E-step launches of one step); None when no capture exists for this workload / GPU count."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
