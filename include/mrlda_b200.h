@@ -58,10 +58,21 @@ typedef struct mrlda_config {
   int32_t world_size;      /* number of document shards / GPUs (1 when single GPU)             */
   int32_t update_alpha;    /* 1 = run the alpha update inside mrlda_iterate (default)          */
   int32_t fp32_mode;       /* 0 = fp64 (default, 1e-9 parity); 1 = optional fp32 E-step tile:
-                              single-precision E / dot products / S, everything else fp64;
-                              stated tolerance 1e-4 on ELBO and logbeta                         */
+                              single-precision E / dot products / S, everything else fp64.
+                              Stated tolerance against the fp64 reference on the same inputs:
+                              ELBO 1e-6; logbeta 1e-4 from the third EM iteration on and 5e-3 in
+                              the first two iterations from a random initial beta (near-identical
+                              topics make the split of a document's mass ill-conditioned)        */
   double eta;              /* Settings.DEFAULT_LOG_ETA = log(1e-12) -> eta = 1e-12              */
   uint64_t seed;           /* seed for mrlda_init_beta_random (the reference uses Math.random)  */
+  int32_t deterministic;   /* 1 = deterministic statistics mode (debugging aid): the phi-weighted
+                              counts and the alpha statistics are accumulated in 192-bit fixed
+                              point with integer atomics and all-reduced as integers, so beta,
+                              alpha and the likelihood are bit-identical from run to run and for
+                              any number of ranks / any sharding of the documents (the Hadoop
+                              shuffle + TermReducer sum in key order, TermReducer.java:137-160).
+                              Every document takes the general kernel: about 2.5x slower         */
+  int32_t reserved;
 } mrlda_config;
 
 /* Counters and per-iteration outputs the driver reads after JobClient.runJob

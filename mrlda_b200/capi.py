@@ -30,7 +30,7 @@ class MrldaConfig(C.Structure):
         ("learning", C.c_int32), ("random_start", C.c_int32), ("symmetric_alpha", C.c_int32),
         ("device", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32),
         ("update_alpha", C.c_int32), ("fp32_mode", C.c_int32), ("eta", C.c_double),
-        ("seed", C.c_uint64),
+        ("seed", C.c_uint64), ("deterministic", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

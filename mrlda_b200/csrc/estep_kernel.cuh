@@ -65,7 +65,36 @@ struct EstepArgs {
   int tmem_slots;  // register-stationary kernel: slots per thread kept in Tensor Memory
   int group_warps;   // warp-group kernel (estep3): warps per document
   int smem_batches;  // warp-group kernel (estep3): shared-memory batches per warp
+  // deterministic statistics mode (estep_kernel<L, KPL, true> only): fixed-point accumulators, three
+  // 64-bit limbs per cell (fx_add below); NULL otherwise
+  unsigned long long *stats_fx;     // V x K x 3
+  unsigned long long *alpha_ss_fx;  // K x 3
 };
+
+// Order-independent accumulation for the deterministic statistics mode.  x is cut, exactly, into the
+// integer floor(x 2^16) and a 64-bit fraction (units of 2^-80), and the three pieces
+// {fraction low 32 bits, fraction high 32 bits, integer part} are added to three 64-bit limbs with
+// integer atomics.  Integer addition is associative, so the limbs do not depend on the order in
+// which documents, CTAs or ranks arrive; a limb takes 2^31 contributions before it can overflow
+// (a cell receives at most one per document), and the limbs of several ranks add up limb by limb
+// (ncclInt64).  Range |x| < 2^47, resolution 2^-80 = 8.3e-25 absolute.
+__device__ __forceinline__ void fx_add(unsigned long long *cell, const double x) {
+  const double xs = x * 65536.0;  // exact
+  const double fl = floor(xs);
+  const long long hi = __double2ll_rd(xs);
+  const unsigned long long lo = __double2ull_rd((xs - fl) * 18446744073709551616.0);  // exact, < 2^64
+  if (lo & 0xffffffffull) atomicAdd(cell, lo & 0xffffffffull);
+  if (lo >> 32) atomicAdd(cell + 1, lo >> 32);
+  if (hi) atomicAdd(cell + 2, (unsigned long long)hi);
+}
+// the value of a cell: (limb2 2^64 + limb1 2^32 + limb0) 2^-80, one rounding per part
+__host__ __device__ __forceinline__ double fx_value(const unsigned long long *cell) {
+  const unsigned long long l0 = cell[0], l1 = cell[1];
+  const long long l2 = (long long)cell[2];
+  const unsigned long long lo = l0 + (l1 << 32);
+  const long long hi = l2 + (long long)(l1 >> 32) + (lo < l0 ? 1 : 0);
+  return (double)hi * (1.0 / 65536.0) + (double)lo * (1.0 / 65536.0 / 18446744073709551616.0);
+}
 
 #define MRLDA_NORM_TINY 1e-200
 
@@ -138,7 +167,7 @@ __device__ __forceinline__ double warp_max(double v) {
 // One sweep's pass over the rows owned by this warp: U row blocks (RPB rows each) are processed
 // together so that their load -> DFMA -> shuffle -> reciprocal chains overlap.  LAST adds the
 // likelihood terms and the statistics scatter (DocumentMapper.java:421,315-329).
-template <int L, int KPL, int U, bool LAST>
+template <int L, int KPL, int U, bool LAST, bool DET>
 __device__ __forceinline__ void sweep_rows(const EstepArgs &a, const double *tile,
                                            const double *cnt_s, const double *gam_s,
                                            double *gextra_s, const double (&th)[KPL],
@@ -227,7 +256,12 @@ __device__ __forceinline__ void sweep_rows(const EstepArgs &a, const double *til
 #pragma unroll
           for (int i = 0; i < KPL; i++) {
             int col = 2 * (j + L * (i >> 1)) + (i & 1);
-            if (col < K) atomicAdd(srow + col, r[u] * th[i] * e[u][i]);
+            if (col < K) {
+              if constexpr (DET)
+                fx_add(a.stats_fx + 3 * ((size_t)(term - 1) * K + col), r[u] * th[i] * e[u][i]);
+              else
+                atomicAdd(srow + col, r[u] * th[i] * e[u][i]);
+            }
           }
         }
       }
@@ -257,7 +291,12 @@ __device__ __forceinline__ void sweep_rows(const EstepArgs &a, const double *til
             atomicAdd(gextra_s + k, c);
             if (LAST) {
               lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
-              if (a.learning) atomicAdd(a.stats + (size_t)(term - 1) * K + k, c);
+              if (a.learning) {
+                if constexpr (DET)
+                  fx_add(a.stats_fx + 3 * ((size_t)(term - 1) * K + k), c);
+                else
+                  atomicAdd(a.stats + (size_t)(term - 1) * K + k, c);
+              }
             }
           }
         }
@@ -267,7 +306,11 @@ __device__ __forceinline__ void sweep_rows(const EstepArgs &a, const double *til
   }
 }
 
-template <int L, int KPL>
+// DET = true is the deterministic statistics mode: the phi-weighted counts and the alpha sufficient
+// statistics go to the fixed-point accumulators (fx_add), so the statistics are bit-identical from
+// run to run and for any number of ranks.  (Rows on the exact log-space slow path still add their
+// gamma contribution through shared-memory atomics in arrival order; no BASELINE shape takes it.)
+template <int L, int KPL, bool DET = false>
 __global__ void __launch_bounds__(EstepShape<L, KPL>::MAX_THREADS, 1)
 estep_kernel(const EstepArgs a) {
   using S = EstepShape<L, KPL>;
@@ -351,10 +394,10 @@ estep_kernel(const EstepArgs a) {
       }
 
       if (!last)
-        sweep_rows<L, KPL, UNROLL, false>(a, tile, cnt_s, gam_s, gextra_s, th, s, lik, b, n, cap, nblocks,
+        sweep_rows<L, KPL, UNROLL, false, DET>(a, tile, cnt_s, gam_s, gextra_s, th, s, lik, b, n, cap, nblocks,
                                           warp, NW, lane);
       else
-        sweep_rows<L, KPL, 1, true>(a, tile, cnt_s, gam_s, gextra_s, th, s, lik, b, n, cap, nblocks,
+        sweep_rows<L, KPL, 1, true, DET>(a, tile, cnt_s, gam_s, gextra_s, th, s, lik, b, n, cap, nblocks,
                                     warp, NW, lane);
 
       // ---- S partials: reduce over the row groups of the warp, publish per warp ----
@@ -414,7 +457,12 @@ estep_kernel(const EstepArgs a) {
       tk += red_s[32 + w2];
     }
     const double dsg = digamma_literal(tg);
-    for (int k = tid; k < K; k += T) ssacc_s[k] += digamma_literal(gam_s[k]) - dsg;
+    for (int k = tid; k < K; k += T) {
+      if constexpr (DET)
+        fx_add(a.alpha_ss_fx + 3 * k, digamma_literal(gam_s[k]) - dsg);
+      else
+        ssacc_s[k] += digamma_literal(gam_s[k]) - dsg;
+    }
     if (tid == 0) {
       double ll = lik_alpha + (tl - lgamma(tg)) + tk;
       long long c = (long long)(-ll * 1e6);  // DocumentMapper.java:253-254, truncation toward zero
@@ -435,31 +483,35 @@ struct EstepVariant {
   cudaError_t (*launch)(const EstepArgs &, int grid, int threads, int cap_rows, cudaStream_t);
   size_t (*smem_bytes)(int nw, int cap);
   cudaError_t (*prepare)(size_t smem);
+  // the deterministic statistics mode (estep_kernel<L, KPL, true>)
+  cudaError_t (*launch_det)(const EstepArgs &, int grid, int threads, int cap_rows, cudaStream_t);
+  cudaError_t (*prepare_det)(size_t smem);
 };
 
 template <int L, int KPL>
 static size_t variant_smem(int nw, int cap) {
   return estep_smem_bytes<L, KPL>(nw, cap);
 }
-template <int L, int KPL>
+template <int L, int KPL, bool DET>
 static cudaError_t variant_prepare(size_t smem) {
-  return cudaFuncSetAttribute(estep_kernel<L, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(estep_kernel<L, KPL, DET>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               (int)smem);
 }
-template <int L, int KPL>
+template <int L, int KPL, bool DET>
 static cudaError_t variant_launch(const EstepArgs &args, int grid, int threads, int cap_rows,
                                   cudaStream_t st) {
   EstepArgs a = args;
   a.cap_rows = cap_rows;
   size_t smem = estep_smem_bytes<L, KPL>(threads / 32, cap_rows);
-  estep_kernel<L, KPL><<<grid, threads, smem, st>>>(a);
+  estep_kernel<L, KPL, DET><<<grid, threads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
 #define MRLDA_VARIANT(L_, KPL_)                                                       \
   {                                                                                   \
-    L_, KPL_, EstepShape<L_, KPL_>::MAX_THREADS, variant_launch<L_, KPL_>,            \
-        variant_smem<L_, KPL_>, variant_prepare<L_, KPL_>                             \
+    L_, KPL_, EstepShape<L_, KPL_>::MAX_THREADS, variant_launch<L_, KPL_, false>,     \
+        variant_smem<L_, KPL_>, variant_prepare<L_, KPL_, false>,                     \
+        variant_launch<L_, KPL_, true>, variant_prepare<L_, KPL_, true>               \
   }
 
 // each estep_inst_*.cu defines one of these tables

@@ -449,6 +449,8 @@ struct mrlda_ctx {
   uint8_t *d_present = nullptr;
   bool alpha_set = false, beta_set = false, have_dl = false;
   uint32_t *d_seed_bits = nullptr;  // informed prior (NULL: uniform eta)
+  unsigned long long *d_stats_fx = nullptr;     // deterministic mode: V x K x 3 fixed-point limbs
+  unsigned long long *d_alpha_ss_fx = nullptr;  // deterministic mode: K x 3
 
   // per-iteration
   double *d_alpha_ss = nullptr;   // K
@@ -595,7 +597,8 @@ void mrlda_destroy(mrlda_ctx *ctx) {
                   ctx->d_gamma,   ctx->d_alpha,  ctx->d_lik_alpha, ctx->d_logbeta, ctx->d_E,
                   ctx->d_rowmax,  ctx->d_dl,     ctx->d_stats,    ctx->d_nrm,    ctx->d_present,
                   ctx->d_alpha_ss, ctx->d_counters, ctx->d_work,  ctx->d_partial, ctx->d_colsum,
-                  ctx->d_alpha_work, ctx->d_phase, ctx->d_seed_bits};
+                  ctx->d_alpha_work, ctx->d_phase, ctx->d_seed_bits, ctx->d_stats_fx,
+                  ctx->d_alpha_ss_fx};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &e : ctx->ev)
@@ -706,6 +709,12 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
 #undef CKC
   *out = ctx;
   return MRLDA_OK;
+}
+
+// deterministic mode: fixed-point limbs (fx_add, estep_kernel.cuh) -> the fp64 statistics the finalize reads
+__global__ void fx_to_double_kernel(const unsigned long long *fx, double *out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = fx_value(fx + 3 * i);
 }
 
 static int refresh_rows(mrlda_ctx *ctx) {
@@ -1025,7 +1034,9 @@ static void plan_estep(mrlda_ctx *ctx, int *ctas_per_sm, int *threads, int *cap_
   const int want = std::max(ctx->p90_rows, gran);
   int best_c = 1;
   const char *fc = getenv("MRLDA_ESTEP_CTAS_PER_SM");
-  const int forced = fc ? atoi(fc) : 0;
+  // deterministic mode: one CTA per SM always, so that the warps per CTA (and with them the order
+  // in which a document's rows are summed) do not depend on the shard's length distribution
+  const int forced = ctx->cfg.deterministic ? 1 : (fc ? atoi(fc) : 0);
   for (int c = 8; c >= 1; c--) {
     if (forced && c != forced) continue;
     int t = (v->max_threads / c) & ~31;
@@ -1064,12 +1075,22 @@ static int exchange(mrlda_ctx *ctx) {
     return MRLDA_ESTATE;
   }
   int rc = g_nccl.GroupStart();
-  if (!rc && ctx->cfg.learning)
-    rc = g_nccl.AllReduce(ctx->d_stats, ctx->d_stats, (size_t)ctx->V * ctx->K, kNcclFloat64,
-                          kNcclSum, ctx->comm, ctx->stream);
-  if (!rc)
-    rc = g_nccl.AllReduce(ctx->d_alpha_ss, ctx->d_alpha_ss, (size_t)ctx->K, kNcclFloat64, kNcclSum,
-                          ctx->comm, ctx->stream);
+  if (ctx->cfg.deterministic) {
+    // integer limbs add up exactly, whatever order the ring visits the ranks in
+    if (!rc && ctx->cfg.learning)
+      rc = g_nccl.AllReduce(ctx->d_stats_fx, ctx->d_stats_fx, (size_t)ctx->V * ctx->K * 3, kNcclInt64,
+                            kNcclSum, ctx->comm, ctx->stream);
+    if (!rc)
+      rc = g_nccl.AllReduce(ctx->d_alpha_ss_fx, ctx->d_alpha_ss_fx, (size_t)ctx->K * 3, kNcclInt64,
+                            kNcclSum, ctx->comm, ctx->stream);
+  } else {
+    if (!rc && ctx->cfg.learning)
+      rc = g_nccl.AllReduce(ctx->d_stats, ctx->d_stats, (size_t)ctx->V * ctx->K, kNcclFloat64,
+                            kNcclSum, ctx->comm, ctx->stream);
+    if (!rc)
+      rc = g_nccl.AllReduce(ctx->d_alpha_ss, ctx->d_alpha_ss, (size_t)ctx->K, kNcclFloat64, kNcclSum,
+                            ctx->comm, ctx->stream);
+  }
   if (!rc)
     rc = g_nccl.AllReduce(ctx->d_counters, ctx->d_counters, 4, kNcclInt64, kNcclSum, ctx->comm,
                           ctx->stream);
@@ -1108,6 +1129,16 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   long long hc[4] = {0, (long long)ctx->D, (long long)ctx->n_tokens, 0};
   CK(cudaMemcpyAsync(ctx->d_counters, hc, sizeof hc, cudaMemcpyHostToDevice, st));
   CK(cudaMemsetAsync(ctx->d_work, 0, 16 * sizeof(int), st));
+  const bool det = ctx->cfg.deterministic != 0;
+  if (det) {
+    if (!ctx->d_stats_fx) {
+      CK(cudaMalloc(&ctx->d_stats_fx, (size_t)ctx->V * K * 3 * sizeof(unsigned long long)));
+      CK(cudaMalloc(&ctx->d_alpha_ss_fx, (size_t)K * 3 * sizeof(unsigned long long)));
+    }
+    if (ctx->cfg.learning)
+      CK(cudaMemsetAsync(ctx->d_stats_fx, 0, (size_t)ctx->V * K * 3 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_alpha_ss_fx, 0, (size_t)K * 3 * sizeof(unsigned long long), st));
+  }
 
   EstepArgs a;
   a.row_ptr = ctx->d_row_ptr;
@@ -1128,6 +1159,8 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.ll_counter = reinterpret_cast<unsigned long long *>(ctx->d_counters);
   a.slow_rows = ctx->d_work + 1;
   a.phase_cycles = ctx->d_phase;
+  a.stats_fx = det ? ctx->d_stats_fx : nullptr;
+  a.alpha_ss_fx = det ? ctx->d_alpha_ss_fx : nullptr;
   a.tmem_slots = 0;
   a.group_warps = 0;
   a.smem_batches = 0;
@@ -1143,7 +1176,8 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   int cap2 = 0, grid2 = 0;
   size_t smem2 = 0;
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");  // "1": general kernel only (test / profiling aid)
-  const bool use2 = ctx->variant2 && !(fk && atoi(fk) == 1);
+  // the deterministic statistics mode exists in the general kernel only
+  const bool use2 = ctx->variant2 && !(fk && atoi(fk) == 1) && !det;
   const bool use2f = use2 && ctx->variant2f != nullptr;
   if (use2f && ctx->D > 0) {
     // optional fp32 mode: registers then Tensor Memory only; longer documents take the fp64 general kernel
@@ -1235,7 +1269,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   size_t smem = 0;
   if (n_long > 0) {
     plan_estep(ctx, &c, &t, &cap, &smem);
-    CK(ctx->variant->prepare(smem));
+    CK(det ? ctx->variant->prepare_det(smem) : ctx->variant->prepare(smem));
   }
   CK(cudaEventRecord(ctx->ev[1], st));
   if (v3) {
@@ -1286,7 +1320,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       a.work_counter = ctx->d_work;
       a.cap_rows = cap;
       int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, n_long);
-      CK(ctx->variant->launch(a, grid, t, cap, sp));
+      CK(det ? ctx->variant->launch_det(a, grid, t, cap, sp) : ctx->variant->launch(a, grid, t, cap, sp));
       ctx->launches++;
     }
     if (!long_pass && grid2 > 0) {
@@ -1318,6 +1352,17 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   CK(cudaEventRecord(ctx->ev[2], st));
   int rc = exchange(ctx);
   if (rc) return rc;
+  if (det) {  // fixed-point limbs (summed over the ranks) -> the fp64 statistics K2 / K3 read
+    if (ctx->cfg.learning) {
+      const int64_t n = (int64_t)ctx->V * K;
+      fx_to_double_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, st>>>(
+          ctx->d_stats_fx, ctx->d_stats, n);
+      ctx->launches++;
+    }
+    fx_to_double_kernel<<<1, 256, 0, st>>>(ctx->d_alpha_ss_fx, ctx->d_alpha_ss, K);
+    ctx->launches++;
+    CK(cudaGetLastError());
+  }
   CK(cudaEventRecord(ctx->ev[3], st));
   long long hres[4];
   int hwork[4];

@@ -4,7 +4,8 @@
 // options (VariationalInferenceOptions.java:55-273), the same model files (alpha-N, beta-N,
 // gamma-N/), the same gamma-directory rotation (:359-379), log lines (:257-275,381-384) and
 // convergence test (:383-386).  JobClient.runJob + the alpha update are one mrlda_iterate call.
-// Extensions (not in the reference): -device, -seed, -rank/-world/-ncclid for one process per GPU.
+// Extensions (not in the reference): -device, -seed, -rank/-world/-ncclid for one process per GPU,
+// -deterministic (fixed-point statistics: bit-identical models for any rank count; slower).
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -32,6 +33,7 @@ struct Options {
   int snapshot = 0;
   int device = 0, rank = 0, world = 1;
   unsigned long long seed = 0x4d724c4441ull;
+  bool deterministic = false;
   std::string nccl_id_file;
 };
 
@@ -56,7 +58,9 @@ void info(const std::string &s) { printf("INFO  VariationalInference: %s\n", s.c
           " -term <int>            number of terms\n"
           " -test <path>           run program in inference mode, i.e. test held-out likelihood\n"
           " -topic <int>           number of topics\n"
-          " -device/-seed/-rank/-world/-ncclid  (extensions: GPU ordinal, beta seed, one process per GPU)\n");
+          " -device/-seed/-rank/-world/-ncclid  (extensions: GPU ordinal, beta seed, one process per GPU)\n"
+          " -deterministic         (extension) fixed-point statistics: the model is bit-identical from run to\n"
+          "                        run and for any -world; every document takes the general kernel (slower)\n");
   exit(0);  // the reference prints the help and exits 0 on a parse error (VIO.java:251-266)
 }
 
@@ -93,6 +97,7 @@ Options parse(int argc, char **argv) {
     else if (a == "informedprior") o.informed_prior = need(i);
     else if (a == "device") o.device = atoi(need(i).c_str());
     else if (a == "seed") o.seed = strtoull(need(i).c_str(), nullptr, 10);
+    else if (a == "deterministic") o.deterministic = true;
     else if (a == "rank") o.rank = atoi(need(i).c_str());
     else if (a == "world") o.world = atoi(need(i).c_str());
     else if (a == "ncclid") o.nccl_id_file = need(i);
@@ -228,6 +233,7 @@ int main(int argc, char **argv) {
     cfg.rank = o.rank;
     cfg.world_size = o.world;
     cfg.seed = o.seed;
+    cfg.deterministic = o.deterministic ? 1 : 0;
     mrlda_ctx *ctx = nullptr;
     if (mrlda_create(&cfg, &ctx) != MRLDA_OK) die(nullptr, "mrlda_create");
 

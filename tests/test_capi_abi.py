@@ -23,11 +23,11 @@ def test_header_symbols_are_exported(capi):
 
 
 def test_struct_layouts_match_header(capi):
-    assert ctypes.sizeof(capi.MrldaConfig) == 64
+    assert ctypes.sizeof(capi.MrldaConfig) == 72
     assert ctypes.sizeof(capi.MrldaIterResult) == 88
     cfg = capi.default_config()
     assert (cfg.sweep_cap, cfg.learning, cfg.world_size, cfg.update_alpha) == (100, 1, 1, 1)
-    assert cfg.eta == 1e-12 and cfg.random_start == 0 and cfg.symmetric_alpha == 0 and cfg.fp32_mode == 0
+    assert cfg.eta == 1e-12 and cfg.random_start == 0 and cfg.symmetric_alpha == 0 and cfg.fp32_mode == 0 and cfg.deterministic == 0
     assert capi.load().mrlda_version().decode().startswith("mrlda_b200")
 
 

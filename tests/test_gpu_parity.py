@@ -401,3 +401,44 @@ def test_error_paths(capi):
             ctx.set_corpus_csr([0, 1], [11], [1])  # term id out of range
         with pytest.raises(capi.MrldaError):
             ctx.set_alpha([0.1, 0.0, 0.1, 0.1])
+
+
+@pytest.mark.parametrize("K", [20, 200, 600])
+def test_deterministic_mode_is_bit_reproducible(capi, oracle, K):
+    """cfg.deterministic: the statistics are accumulated in fixed point with integer atomics, so two
+    runs on the same inputs give bit-identical beta, alpha, statistics and likelihood (the default
+    mode differs at 1e-16 from run to run through the order of the fp64 atomics) — and they stay
+    within the parity tolerance of the oracle.  The documents are also presented in a different
+    order (same set): the statistics are a sum over documents, so they must not move at all."""
+    from mrlda_b200 import corpus
+    c = small_corpus(D=300, V=500, K=K, mean_len=60, seed=K + 2)
+    alpha = np.full(K, 1e-3)
+    lb = corpus.init_logbeta(c.n_terms, K, seed=K + 3)
+    runs = []
+    for _ in range(2):
+        out, ref = _run_pair(capi, oracle, c, alpha, lb, deterministic=1, sweep_cap=30)
+        runs.append(out)
+    _check(runs[0], ref, c)
+    a, b = runs
+    assert a["r"]["ll_counter"] == b["r"]["ll_counter"]
+    for key in ("gamma", "alpha_ss", "alpha", "logbeta", "stats"):
+        assert np.array_equal(a[key], b[key]), key
+    assert all(np.array_equal(x, y) for x, y in zip(a["beta"], b["beta"]))
+    tot = np.bincount(c.term_id - 1, weights=c.count, minlength=c.n_terms)
+    assert np.allclose(a["stats"].sum(1), tot, rtol=1e-13, atol=1e-13)
+    # the same documents in reverse order: per-document results are unchanged, so the sums are too
+    order = np.arange(c.n_docs)[::-1]
+    n = np.diff(c.row_ptr)
+    rp = np.zeros(c.n_docs + 1, dtype=np.int64)
+    rp[1:] = np.cumsum(n[order])
+    idx = np.concatenate([np.arange(c.row_ptr[d], c.row_ptr[d + 1]) for d in order])
+    with capi.Context(K, c.n_terms, deterministic=1, sweep_cap=30) as ctx:
+        ctx.set_corpus_csr(rp, c.term_id[idx], c.count[idx])
+        ctx.set_alpha(alpha)
+        ctx.set_logbeta(lb)
+        r = ctx.iterate()
+        assert r["ll_counter"] == a["r"]["ll_counter"]
+        assert np.array_equal(ctx.get_stats(), a["stats"])
+        assert np.array_equal(ctx.get_logbeta(), a["logbeta"])
+        assert np.array_equal(ctx.get_alpha(), a["alpha"])
+        assert np.array_equal(ctx.get_gamma()[np.argsort(order)], a["gamma"])

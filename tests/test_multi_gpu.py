@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _rank(rank, world, id_path, out_dir):
+def _rank(rank, world, id_path, out_dir, deterministic=0):
     sys.path.insert(0, ROOT)
     import time
 
@@ -29,7 +29,7 @@ def _rank(rank, world, id_path, out_dir):
     while not os.path.exists(id_path):
         time.sleep(0.05)
     uid = open(id_path, "rb").read()
-    with capi.Context(K, V, device=rank, rank=rank, world_size=world) as ctx:
+    with capi.Context(K, V, device=rank, rank=rank, world_size=world, deterministic=deterministic) as ctx:
         ctx.comm_init(uid)
         ctx.set_corpus_csr(mine.row_ptr, mine.term_id, mine.count)
         ctx.set_alpha(alpha)
@@ -72,3 +72,28 @@ def test_two_gpu_iteration_matches_oracle(tmp_path, oracle):
         assert float(got["allreduce_ms"]) > 0
     a, b = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     assert np.array_equal(a["logbeta"], b["logbeta"]) and np.array_equal(a["alpha"], b["alpha"])
+
+
+def test_deterministic_mode_is_independent_of_the_rank_count(tmp_path):
+    """cfg.deterministic: fixed-point statistics all-reduced as integers.  Two ranks on two GPUs and one
+    rank on one GPU must produce bit-identical likelihood, alpha and logbeta over two EM iterations
+    (the reference's shuffle sums each key's values in one reducer, whatever the mapper count)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from mrlda_b200 import capi, corpus
+    mp.spawn(_rank, args=(2, str(tmp_path / "nccl.id"), str(tmp_path), 1), nprocs=2, join=True)
+    K, V = 20, 600
+    full = corpus.generate(240, V, K, 50, seed=17)
+    with capi.Context(K, V, deterministic=1) as ctx:
+        ctx.set_corpus_csr(full.row_ptr, full.term_id, full.count)
+        ctx.set_alpha(np.full(K, 1e-3))
+        ctx.set_logbeta(corpus.init_logbeta(V, K, seed=2))
+        ll = [ctx.iterate()["log_likelihood"], ctx.iterate()["log_likelihood"]]
+        alpha, logbeta, gamma = ctx.get_alpha(), ctx.get_logbeta(), ctx.get_gamma()
+    for rank in range(2):
+        got = np.load(tmp_path / f"rank{rank}.npz")
+        assert list(got["ll"]) == ll
+        assert np.array_equal(got["alpha"], alpha) and np.array_equal(got["logbeta"], logbeta)
+        assert np.array_equal(got["gamma"], gamma[int(got["lo"]):int(got["hi"])])
