@@ -22,8 +22,12 @@
 //     barrier and no shared-memory exchange per row.  S_c accumulates per lane over the warp's rows.
 //   * A warp's batches live, in this order, in REGISTERS (the first R batches), in TENSOR MEMORY
 //     (the next T batches: thread-private tcgen05.st / tcgen05.ld, no MMA; the NW/4 warps that
-//     share a lane quarter split the 512 columns), and in a thread-private, lane-interleaved
-//     region of SHARED MEMORY (the last M batches).
+//     share a lane quarter split the 512 columns), and in SHARED MEMORY (the last M batches).  A
+//     shared-memory batch is the RPB x KS row-major tile that one TMA tile::gather4 copy
+//     (UTMALDG.2D.GATHER4: four rows of the term-major E matrix picked by term id) writes: lane 0
+//     of the warp issues the copies, they complete on the warp's mbarrier while all 32 lanes load
+//     the register and Tensor Memory batches; the L lanes of a row read 16 L contiguous bytes per
+//     LDS.128, so the row-major tile is bank-conflict free.
 //   * Per sweep and warp.  Pass A: theta in registers; partial dot products of every batch (TMEM
 //     batches are fetched in two parts so that one tcgen05.ld is always in flight behind the
 //     DFMAs).  Then the L-lane butterflies and the reciprocals of ALL batches as independent,
@@ -83,7 +87,7 @@ struct Estep3Halves {
 template <int L, int KPL, int R, int NW>
 struct Estep3Smem {
   using S = Estep3Shape<L, KPL, R, NW>;
-  size_t tile, spart, theta, gam, gextra, alpha, ssacc, cnt, red, meta, total;
+  size_t tile, spart, theta, gam, gextra, alpha, ssacc, cnt, red, meta, mbar, total;
   __host__ __device__ Estep3Smem(int M, int G) {
     const int NG = NW / G;
     size_t o = 0;
@@ -97,6 +101,7 @@ struct Estep3Smem {
     cnt = o;    o += (size_t)NW * S::NBMAX * S::RPB;  // n_w of every batch slot (0: padding)
     red = o;    o += NW * 4;
     meta = o;   o += 10;  // 20 ints: [0] TMEM base, [1 + group] document
+    mbar = o;   o += 2 * NW;  // per warp: the mbarrier its TMA row gathers complete on, and its phase parity
     total = o * sizeof(double);
   }
 };
@@ -122,26 +127,40 @@ __device__ __forceinline__ void estep3_load_cols(const double *row, const int j,
   }
   if constexpr (KPL & 1) v[KPL - 1] = GLOBAL ? __ldg(row + 2 * L * HP + j) : row[2 * L * HP + j];
 }
-// A batch of the thread-private, lane-interleaved shared-memory region: [HP][32] double2, [32] double
-template <int KPL>
-__device__ __forceinline__ void estep3_tile_ld(const double *batch, const int lane, double (&v)[KPL]) {
-  constexpr int HP = KPL / 2;
-  const double2 *src = reinterpret_cast<const double2 *>(batch) + lane;
-#pragma unroll
-  for (int i = 0; i < HP; i++) {
-    const double2 t2 = src[(size_t)i * 32];
-    v[2 * i] = t2.x;
-    v[2 * i + 1] = t2.y;
-  }
-  if constexpr (KPL & 1) v[KPL - 1] = batch[HP * 64 + lane];
+// A shared-memory batch is the [RPB][KS] row-major tile a TMA gather writes; lane (g, j) reads its
+// KPL columns of row g exactly as it reads a row of E or theta.
+template <int L, int KPL>
+__device__ __forceinline__ void estep3_tile_ld(const double *batch, const int g, const int j, double (&v)[KPL]) {
+  estep3_load_cols<L, KPL, false>(batch + (size_t)g * (L * KPL), j, v);
 }
-template <int KPL>
-__device__ __forceinline__ void estep3_tile_st(double *batch, const int lane, const double (&v)[KPL]) {
-  constexpr int HP = KPL / 2;
-  double2 *dst = reinterpret_cast<double2 *>(batch) + lane;
-#pragma unroll
-  for (int i = 0; i < HP; i++) dst[(size_t)i * 32] = make_double2(v[2 * i], v[2 * i + 1]);
-  if constexpr (KPL & 1) batch[HP * 64 + lane] = v[KPL - 1];
+
+// mbarrier + TMA tile::gather4 (sm_100a): four rows of the 2-D tensor behind `tmap` (the term-major E
+// matrix, box = KS columns x 1 row), picked by their row indices, land as a [4][KS] tile at dst.
+__device__ __forceinline__ uint32_t estep3_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void estep3_mbar_init(unsigned long long *mbar, const int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(estep3_smem_u32(mbar)), "r"(count));
+}
+__device__ __forceinline__ void estep3_mbar_expect(unsigned long long *mbar, const uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(estep3_smem_u32(mbar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void estep3_mbar_wait(unsigned long long *mbar, const uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(estep3_smem_u32(mbar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void estep3_tma_gather4(double *dst, const void *tmap, unsigned long long *mbar,
+                                                   const int r0, const int r1, const int r2, const int r3) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
+      "%4, %5, %6}], [%7];" ::"r"(estep3_smem_u32(dst)),
+      "l"(tmap), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(estep3_smem_u32(mbar))
+      : "memory");
 }
 
 // n_w phi_wk = r_w theta_k E_wk into the K x V statistics (DocumentMapper.java:315-329)
@@ -318,7 +337,7 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
 #pragma unroll
     for (int m = 0; m < NSM; m++) {
       double ev[KPL];
-      estep3_tile_ld<KPL>(w.tile_w + (size_t)m * 32 * KPL, lane, ev);
+      estep3_tile_ld<L, KPL>(w.tile_w + (size_t)m * 32 * KPL, w.g, j, ev);
       double ac[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int c = 0; c < KPL; c++) ac[c & 3] = fma(th[c], ev[c], ac[c & 3]);
@@ -354,7 +373,7 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
 #pragma unroll
   for (int m = 0; m < NSM; m++) {
     double ev[KPL];
-    estep3_tile_ld<KPL>(w.tile_w + (size_t)m * 32 * KPL, lane, ev);
+    estep3_tile_ld<L, KPL>(w.tile_w + (size_t)m * 32 * KPL, w.g, j, ev);
     const double r = rr[R + NTM + m];
 #pragma unroll
     for (int c = 0; c < KPL; c++) s[c] = fma(r, ev[c], s[c]);
@@ -419,7 +438,7 @@ __device__ __forceinline__ void estep3_sweep_last(const EstepArgs &a, const Este
 #pragma unroll 1
   for (int m = 0; R + T + m < nb; m++) {
     double ev[KPL];
-    estep3_tile_ld<KPL>(w.tile_w + (size_t)m * 32 * KPL, w.g * L + w.j, ev);
+    estep3_tile_ld<L, KPL>(w.tile_w + (size_t)m * 32 * KPL, w.g, w.j, ev);
     estep3_last_batch<L, KPL>(a, w.theta_g, w.cnt_w, ev, R + T + m, zrow0, w.g, w.j, s, lik, badbits);
   }
 }
@@ -601,7 +620,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int RPB = S::RPB, KS = S::KS, TW = S::TW, T = S::T, NBMAX = S::NBMAX;
   constexpr int THREADS = S::THREADS;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int K = a.K;
@@ -632,6 +651,14 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
   double *ssacc_s = smem + lay.ssacc;
   double *red_s = smem + lay.red;  // [warp][4]
   int *meta_s = reinterpret_cast<int *>(smem + lay.meta);  // [0] TMEM base, [1 + grp] document
+  // per warp, in shared memory so that nothing of it stays in registers across the sweep loops:
+  // [2 warp] the mbarrier its TMA row gathers complete on, [2 warp + 1] the parity of its next phase
+  if (lane == 0) {
+    unsigned long long *mb = reinterpret_cast<unsigned long long *>(smem + lay.mbar) + 2 * warp;
+    estep3_mbar_init(mb, 1);
+    mb[1] = 0ull;
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
   for (int k = tid; k < KS; k += THREADS) {
     q.alpha_s[k] = k < K ? a.alpha[k] : 1.0;
@@ -671,6 +698,26 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
     // are a copy of the document's last row with n_w = 0. ----
     for (int x = lane; x < NBMAX * RPB; x += 32) cnt_w[x] = 0.0;
     __syncwarp();
+    // shared-memory batches first: lane 0 hands them to the TMA unit (one gather4 per batch: the
+    // four rows are picked by term id), the copies run while the warp loads its other batches
+    const int nsm = nb > R + T ? nb - (R + T) : 0;  // warp-uniform
+    unsigned long long *mbar_w = reinterpret_cast<unsigned long long *>(smem + lay.mbar) + 2 * warp;
+    if (nsm > 0 && lane == 0) {
+      static_assert(RPB == 4, "tile::gather4 fetches the four rows of a batch");
+      // the previous document's reads of this tile (generic proxy) are ordered before the copies
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      estep3_mbar_expect(mbar_w, (uint32_t)(nsm * RPB * KS * sizeof(double)));
+      for (int m = 0; m < nsm; m++) {
+        const int row0 = (bstart + R + T + m) * RPB;
+        int id[4];
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+          const int row = row0 + (x < RPB ? x : RPB - 1);
+          id[x] = __ldg(a.term_id + b + (row < n ? row : n - 1)) - 1;
+        }
+        estep3_tma_gather4(tile_w + (size_t)m * 32 * KPL, a.tmap_E, mbar_w, id[0], id[1], id[2], id[3]);
+      }
+    }
     double e[S::RA][KPL];
 #pragma unroll
     for (int bi = 0; bi < NBMAX; bi++) {
@@ -679,22 +726,22 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
         const int row = (bstart + bi) * RPB + w.g;
         const bool valid = bi < nb && row < n;
         const int rowc = valid ? row : n - 1;
-        double v[KPL];
-        estep3_load_cols<L, KPL, true>(a.E + (size_t)(__ldg(a.term_id + b + rowc) - 1) * a.e_stride, w.j, v);
         if (valid && w.j == 0) cnt_w[bi * RPB + w.g] = (double)__ldg(a.count + b + row);
-        if (bi < R) {
+        if (bi < R + T) {
+          double v[KPL];
+          estep3_load_cols<L, KPL, true>(a.E + (size_t)(__ldg(a.term_id + b + rowc) - 1) * a.e_stride, w.j, v);
+          if (bi < R) {
 #pragma unroll
-          for (int c = 0; c < KPL; c++) e[bi < R ? bi : 0][c] = v[c];
-        } else if (bi < R + T) {
-          uint32_t w32[TW];
+            for (int c = 0; c < KPL; c++) e[bi < R ? bi : 0][c] = v[c];
+          } else {
+            uint32_t w32[TW];
 #pragma unroll
-          for (int c = 0; c < KPL; c++) {
-            w32[2 * c] = (uint32_t)__double2loint(v[c]);
-            w32[2 * c + 1] = (uint32_t)__double2hiint(v[c]);
+            for (int c = 0; c < KPL; c++) {
+              w32[2 * c] = (uint32_t)__double2loint(v[c]);
+              w32[2 * c + 1] = (uint32_t)__double2hiint(v[c]);
+            }
+            tmem_st_words<TW>(w.tbase + (uint32_t)(bi - R) * TW, w32);
           }
-          tmem_st_words<TW>(w.tbase + (uint32_t)(bi - R) * TW, w32);
-        } else {
-          estep3_tile_st<KPL>(tile_w + (size_t)(bi - R - T) * 32 * KPL, lane, v);
         }
       }
     }
@@ -707,6 +754,12 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
         q.gam_g[col] = gam;
         q.theta_g[col] = exp_digamma(gam);
       }
+    }
+    if (nsm > 0) {  // the TMA copies of this warp's shared-memory batches have landed
+      const uint32_t parity = (uint32_t)mbar_w[1];
+      estep3_mbar_wait(mbar_w, parity);
+      __syncwarp();
+      if (lane == 0) mbar_w[1] = parity ^ 1u;
     }
     estep3_group_sync(q.bar_id, GT);
 

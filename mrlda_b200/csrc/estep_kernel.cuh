@@ -67,6 +67,7 @@ struct EstepArgs {
   int smem_batches;  // warp-group kernel (estep3): shared-memory batches per warp
   // deterministic statistics mode (estep_kernel<L, KPL, true> only): fixed-point accumulators, three
   // 64-bit limbs per cell (fx_add below); NULL otherwise
+  const void *tmap_E;  // warp-group kernel (estep3): CUtensorMap of E in global memory (TMA row gathers)
   unsigned long long *stats_fx;     // V x K x 3
   unsigned long long *alpha_ss_fx;  // K x 3
 };

@@ -24,6 +24,8 @@
 
 #include "../../include/mrlda_b200.h"
 #include "estep2f_kernel.cuh"
+#include <cuda.h>  // CUtensorMap types only; the encoder is looked up through the runtime (no -lcuda)
+
 #include "estep3_kernel.cuh"
 
 using namespace mrlda;
@@ -449,6 +451,7 @@ struct mrlda_ctx {
   uint8_t *d_present = nullptr;
   bool alpha_set = false, beta_set = false, have_dl = false;
   uint32_t *d_seed_bits = nullptr;  // informed prior (NULL: uniform eta)
+  void *d_tmap_E = nullptr;  // CUtensorMap of E (TMA row gathers of the warp-group kernel)
   unsigned long long *d_stats_fx = nullptr;     // deterministic mode: V x K x 3 fixed-point limbs
   unsigned long long *d_alpha_ss_fx = nullptr;  // deterministic mode: K x 3
 
@@ -598,7 +601,7 @@ void mrlda_destroy(mrlda_ctx *ctx) {
                   ctx->d_rowmax,  ctx->d_dl,     ctx->d_stats,    ctx->d_nrm,    ctx->d_present,
                   ctx->d_alpha_ss, ctx->d_counters, ctx->d_work,  ctx->d_partial, ctx->d_colsum,
                   ctx->d_alpha_work, ctx->d_phase, ctx->d_seed_bits, ctx->d_stats_fx,
-                  ctx->d_alpha_ss_fx};
+                  ctx->d_alpha_ss_fx, ctx->d_tmap_E};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   for (auto &e : ctx->ev)
@@ -686,6 +689,33 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   CKC(cudaMalloc(&ctx->d_logbeta, V * K * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_E, V * KS * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_rowmax, V * sizeof(double)));
+  if (ctx->variant3) {
+    // Tensor map of E for the warp-group kernel's TMA tile::gather4 copies: a 2-D fp64 tensor
+    // {columns, terms}, box = one row of the kernel's KS columns (the gather picks four rows).
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+    EncodeFn encode = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
+    const cuuint32_t ks3 = (cuuint32_t)(ctx->variant3->L * ctx->variant3->KPL);
+    alignas(64) CUtensorMap tm;
+    const cuuint64_t gdim[2] = {(cuuint64_t)ks3, (cuuint64_t)V};
+    const cuuint64_t gstride[1] = {(cuuint64_t)KS * sizeof(double)};
+    const cuuint32_t box[2] = {ks3, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult trc = encode ? encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ctx->d_E, gdim, gstride, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+                                : CUDA_ERROR_NOT_SUPPORTED;
+    if (trc != CUDA_SUCCESS) {
+      set_err(ctx, "mrlda_create: cuTensorMapEncodeTiled failed (%d)", (int)trc);
+      return fail(MRLDA_ECUDA);
+    }
+    CKC(cudaMalloc(&ctx->d_tmap_E, sizeof tm));
+    CKC(cudaMemcpy(ctx->d_tmap_E, &tm, sizeof tm, cudaMemcpyHostToDevice));
+  }
   CKC(cudaMalloc(&ctx->d_dl, V * K * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_stats, V * K * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_nrm, K * sizeof(float)));
@@ -1159,6 +1189,7 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   a.ll_counter = reinterpret_cast<unsigned long long *>(ctx->d_counters);
   a.slow_rows = ctx->d_work + 1;
   a.phase_cycles = ctx->d_phase;
+  a.tmap_E = ctx->d_tmap_E;
   a.stats_fx = det ? ctx->d_stats_fx : nullptr;
   a.alpha_ss_fx = det ? ctx->d_alpha_ss_fx : nullptr;
   a.tmem_slots = 0;
