@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--sweep-cap", type=int, default=100)
     ap.add_argument("--fp32", action="store_true", help="optional fp32 mode")
     ap.add_argument("--no-learning", action="store_true", help="test mode: no statistics scatter")
+    ap.add_argument("--deterministic", action="store_true", help="deterministic statistics mode")
     args = ap.parse_args()
     D0, V, K, mean_len, heavy = corpus.SHAPES[args.workload]
     c = corpus.generate(args.docs, V, K, mean_len, seed=4, heavy_tail=heavy, device="cuda")
@@ -37,7 +38,7 @@ def main():
         c = corpus.Corpus(rp, c.term_id[idx], c.count[idx], V, K)
     n = np.diff(c.row_ptr)
     with capi.Context(K, V, sweep_cap=args.sweep_cap, fp32_mode=int(args.fp32),
-                      learning=0 if args.no_learning else 1) as ctx:
+                      learning=0 if args.no_learning else 1, deterministic=int(args.deterministic)) as ctx:
         ctx.set_corpus_csr(c.row_ptr, c.term_id, c.count)
         ctx.set_alpha(np.full(K, 1e-3))
         ctx.set_logbeta(corpus.init_logbeta(V, K, seed=7))
