@@ -22,7 +22,8 @@
 //   * CL > 1: a thread-block cluster of CL CTAs (one per SM) owns the document; the topic split
 //     continues across the CTAs (CTA r, warp w owns columns [(r*NW+w)*CPW, +CPW)), so K up to
 //     CL*NW*CPW = 1024 fits on chip.  The only cross-CTA traffic is the per-row partial dot products,
-//     read through distributed shared memory after one cluster barrier per sweep.
+//     read through distributed shared memory after one cluster barrier per sweep, and the document
+//     index the leader CTA pulls from the work queue.
 //   * WPS = warps per SM the variant is compiled for: 8 (255 registers per thread, most of the tile
 //     in registers) or 16 (128 registers per thread, more of the tile in shared memory, twice the
 //     warps to hide the FP64 / shared-memory latencies of the serial phases).
@@ -33,6 +34,8 @@
 //     those of the last, partially filled slot.
 #pragma once
 #include <cooperative_groups.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "estep_kernel.cuh"
 #include "tmem_ops.cuh"
@@ -626,6 +629,8 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
   }
   if (tid == 0) meta_s[1] = 0;
   double *theta_w = theta_s + warp * CPW;
+  // no CTA may write into a peer's shared memory before that peer has started
+  if constexpr (CL > 1) cg::this_cluster().sync();
 
   int round = 0;
   for (;;) {
@@ -635,8 +640,18 @@ __global__ void __launch_bounds__(NW * 32, WPS / NW) estep2_kernel(const EstepAr
       if (tid == 0) meta_s[0] = a.doc_begin + atomicAdd(a.work_counter, 1);
       __syncthreads();
       qi = meta_s[0];
-    } else {  // all CTAs of a cluster must agree on the document: static round-robin over clusters
-      qi = a.doc_begin + (int)(blockIdx.x / CL) + round * (int)(gridDim.x / CL);
+    } else {
+      // all CTAs of a cluster must agree on the document: the leader CTA pulls it from the launch's
+      // work queue and writes it into every CTA's shared memory.  Two slots, used in turn: the
+      // leader can only write slot r again after the cluster barrier of round r + 1, which every
+      // thread reaches after it has read slot r.
+      if (crank == 0 && tid == 0) {
+        const int v = a.doc_begin + atomicAdd(a.work_counter, 1);
+#pragma unroll
+        for (int r = 0; r < CL; r++) cg::this_cluster().map_shared_rank(meta_s, r)[4 + (round & 1)] = v;
+      }
+      cg::this_cluster().sync();
+      qi = meta_s[4 + (round & 1)];
       round++;
     }
     if (qi >= a.doc_end) break;
@@ -862,14 +877,18 @@ static cudaError_t variant2_launch(const EstepArgs &args, int grid, int cap_rows
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    // documents are dealt round-robin to the clusters of the grid, so every cluster must be
-    // resident from the start: clamp the grid to what the GPU can co-schedule (cluster placement
-    // leaves some SMs unused: 132 of 148 CTAs at cluster size 4)
+    // persistent clusters pulling documents from the launch's work queue: no more clusters than the
+    // GPU can co-schedule (cluster placement leaves some SMs unused: 132 of 148 CTAs at cluster
+    // size 4)
     int max_clusters = 0;
     cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, estep2_kernel<NW, CPW, RREG, WPS, CL>, &cfg);
     if (e != cudaSuccess) return e;
     if (max_clusters < 1) return cudaErrorLaunchOutOfResources;
-    if (grid / CL > max_clusters) cfg.gridDim = dim3((unsigned)(max_clusters * CL));
+    if (getenv("MRLDA_DEBUG"))
+      fprintf(stderr, "estep2<%d,%d,%d,%d,%d>: grid %d CTAs, smem %zu, cap %d rows, max active clusters %d\n",
+              NW, CPW, RREG, WPS, CL, grid, smem, cap_rows, max_clusters);
+    if (grid / CL > max_clusters && !getenv("MRLDA_NO_CLUSTER_CLAMP"))
+      cfg.gridDim = dim3((unsigned)(max_clusters * CL));
     return cudaLaunchKernelEx(&cfg, estep2_kernel<NW, CPW, RREG, WPS, CL>, a);
   }
 }
@@ -880,12 +899,16 @@ static cudaError_t variant2_launch(const EstepArgs &args, int grid, int cap_rows
         variant2_prepare<NW_, CPW_, RREG_, WPS_, 1>                                                 \
   }
 #define MRLDA_VARIANT2(NW_, CPW_, WPS_) MRLDA_VARIANT2R(NW_, CPW_, estep2_rreg(CPW_, WPS_), WPS_)
-// cluster variants: 8 warps x 255 registers per CTA, CL CTAs per document
-#define MRLDA_VARIANT2C(CPW_, CL_)                                                                   \
-  {                                                                                                  \
-    8, CPW_, estep2_rreg(CPW_, 8), 8, CL_, variant2_launch<8, CPW_, estep2_rreg(CPW_, 8), 8, CL_>,   \
-        variant2_smem<8, CPW_>, variant2_prepare<8, CPW_, estep2_rreg(CPW_, 8), 8, CL_>              \
+// cluster variants: CL CTAs of NW warps x 255 registers per document, one CTA per SM.  (4-warp CTAs
+// at twice the cluster size put two documents on every SM but hold the same number of documents
+// on the GPU: measured equal, and not instantiated.)
+#define MRLDA_VARIANT2CN(NW_, CPW_, CL_)                                                   \
+  {                                                                                        \
+    NW_, CPW_, estep2_rreg(CPW_, 8), 8, CL_,                                               \
+        variant2_launch<NW_, CPW_, estep2_rreg(CPW_, 8), 8, CL_>, variant2_smem<NW_, CPW_>, \
+        variant2_prepare<NW_, CPW_, estep2_rreg(CPW_, 8), 8, CL_>                          \
   }
+#define MRLDA_VARIANT2C(CPW_, CL_) MRLDA_VARIANT2CN(8, CPW_, CL_)
 
 extern const Estep2Variant g_estep2_variants_W1[];
 extern const int g_estep2_variants_W1_n;
@@ -899,5 +922,10 @@ extern const Estep2Variant g_estep2_variants_C2[];
 extern const int g_estep2_variants_C2_n;
 extern const Estep2Variant g_estep2_variants_C4[];
 extern const int g_estep2_variants_C4_n;
+// the wide cluster class: twice the cluster size at half the column slice (longer documents)
+extern const Estep2Variant g_estep2_variants_X4[];
+extern const int g_estep2_variants_X4_n;
+extern const Estep2Variant g_estep2_variants_X8[];
+extern const int g_estep2_variants_X8_n;
 
 }  // namespace mrlda

@@ -27,6 +27,7 @@
 #include <cuda.h>  // CUtensorMap types only; the encoder is looked up through the runtime (no -lcuda)
 
 #include "estep3_kernel.cuh"
+#include "estep3c_kernel.cuh"
 
 using namespace mrlda;
 
@@ -423,7 +424,12 @@ struct mrlda_ctx {
   const EstepVariant *variant = nullptr;    // general kernel (any document length)
   const Estep2Variant *variant2 = nullptr;  // register-stationary kernel (documents that fit one SM)
   const Estep2fVariant *variant2f = nullptr;  // fp32-mode counterpart of variant2 (same NW, CPW)
+  // second cluster class beside variant2 when it is a cluster variant (K > 256): twice the cluster
+  // size at half the column slice, for documents longer than variant2 holds
+  const Estep2Variant *variant2_wide = nullptr;
   const Estep3Variant *variant3 = nullptr;  // warp-group kernel (several documents in flight per SM)
+  // warp-group kernel with the topics split across a cluster (K > 208); takes the place of variant3
+  const Estep3cVariant *variant3c = nullptr;
   int ES = 0;                               // row stride of E in doubles
   std::vector<int32_t> h_nnz_sorted;        // nnz per document in doc_order (descending)
   int num_sms = 0;
@@ -458,7 +464,7 @@ struct mrlda_ctx {
   // per-iteration
   double *d_alpha_ss = nullptr;   // K
   long long *d_counters = nullptr; // [0] ll counter, [1] n_docs, [2] n_tokens, [3] slow rows
-  int *d_work = nullptr;           // [0] work queue, [1] slow rows, [2..3] estep2, [4..7] estep3 classes
+  int *d_work = nullptr;           // [0] work queue, [1] slow rows, [2] estep2f, [4..9] estep3 classes, [10..15] estep2 classes
   long long *d_phase = nullptr;    // phase cycle counters (MRLDA_PHASE_TIMING builds)
   double *d_partial = nullptr, *d_colsum = nullptr, *d_alpha_work = nullptr;
   int nslabs = 0, slab = 0;
@@ -542,6 +548,21 @@ static const Estep2Variant *select_variant2(int K) {
   return best;
 }
 
+// The wide cluster class of a cluster variant (see mrlda_ctx::variant2_wide).
+static const Estep2Variant *select_cluster_wide(const Estep2Variant *base, int K) {
+  if (!base || base->CL < 2 || base->CL > 4) return nullptr;
+  const Estep2Variant *tab = base->CL == 2 ? g_estep2_variants_X4 : g_estep2_variants_X8;
+  const int n = base->CL == 2 ? g_estep2_variants_X4_n : g_estep2_variants_X8_n;
+  const Estep2Variant *best = nullptr;
+  for (int i = 0; i < n; i++) {
+    const Estep2Variant *v = &tab[i];
+    // same padded topic count as the base variant: E has one row stride
+    if (v->CL * v->NW * v->CPW < K || v->CL * v->NW * v->CPW > base->CL * base->NW * base->CPW) continue;
+    if (!best || v->CPW < best->CPW) best = v;
+  }
+  return best;
+}
+
 // Warp-group kernel: narrowest row (L * KPL >= K).  MRLDA_ESTEP_KERNEL=2 (register-stationary
 // kernel of round 1) or =1 (general kernel only) switch it off for A/B runs.
 static const Estep3Variant *select_variant3(int K) {
@@ -557,6 +578,24 @@ static const Estep3Variant *select_variant3(int K) {
       if (v->L * v->KPL < K || v->NW != want_nw) continue;
       if (!best || v->L * v->KPL < best->L * best->KPL) best = v;
     }
+  return best;
+}
+
+// Cluster warp-group kernel: fewest padded topics (CL * L * KPL >= K), then the smallest cluster.
+// MRLDA_ESTEP_KERNEL=1 / 2 switch it off like the single-CTA one.
+static const Estep3cVariant *select_variant3c(int K) {
+  const char *fk = getenv("MRLDA_ESTEP_KERNEL");
+  if (fk && (atoi(fk) == 1 || atoi(fk) == 2)) return nullptr;
+  const Estep3cVariant *best = nullptr;
+  for (int i = 0; i < g_estep3c_variants_n; i++) {
+    const Estep3cVariant *v = &g_estep3c_variants[i];
+    const int ks = v->CL * v->v.L * v->v.KPL;
+    // every CTA of the cluster must own at least one topic
+    if (ks < K || (v->CL - 1) * v->v.L * v->v.KPL >= K) continue;
+    if (!best || ks < best->CL * best->v.L * best->v.KPL ||
+        (ks == best->CL * best->v.L * best->v.KPL && v->CL < best->CL))
+      best = v;
+  }
   return best;
 }
 
@@ -652,11 +691,15 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   ctx->KS = ctx->variant->L * ctx->variant->KPL;
   ctx->variant2 = select_variant2(ctx->K);
   ctx->variant2f = cfg->fp32_mode ? select_variant2f(ctx->variant2) : nullptr;
+  if (!cfg->fp32_mode) ctx->variant2_wide = select_cluster_wide(ctx->variant2, ctx->K);
   ctx->ES = ctx->KS;
   if (ctx->variant2)
     ctx->ES = std::max(ctx->ES, ctx->variant2->CL * ctx->variant2->NW * ctx->variant2->CPW);
   ctx->variant3 = cfg->fp32_mode ? nullptr : select_variant3(ctx->K);
   if (ctx->variant3) ctx->ES = std::max(ctx->ES, ctx->variant3->L * ctx->variant3->KPL);
+  if (!ctx->variant3 && !cfg->fp32_mode) ctx->variant3c = select_variant3c(ctx->K);
+  if (ctx->variant3c)
+    ctx->ES = std::max(ctx->ES, ctx->variant3c->CL * ctx->variant3c->v.L * ctx->variant3c->v.KPL);
   auto fail = [&](int code) {
     g_global_error = ctx->err;
     mrlda_destroy(ctx);
@@ -689,7 +732,7 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
   CKC(cudaMalloc(&ctx->d_logbeta, V * K * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_E, V * KS * sizeof(double)));
   CKC(cudaMalloc(&ctx->d_rowmax, V * sizeof(double)));
-  if (ctx->variant3) {
+  if (ctx->variant3 || ctx->variant3c) {
     // Tensor map of E for the warp-group kernel's TMA tile::gather4 copies: a 2-D fp64 tensor
     // {columns, terms}, box = one row of the kernel's KS columns (the gather picks four rows).
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -699,9 +742,11 @@ int mrlda_create(const mrlda_config *cfg, mrlda_ctx **out) {
     EncodeFn encode = nullptr;
     cudaDriverEntryPointQueryResult qres;
     CKC(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &qres));
-    const cuuint32_t ks3 = (cuuint32_t)(ctx->variant3->L * ctx->variant3->KPL);
+    // (the cluster kernel's CTA r gathers the columns [r ks3, (r + 1) ks3) of the rows)
+    const Estep3Variant *v3 = ctx->variant3 ? ctx->variant3 : &ctx->variant3c->v;
+    const cuuint32_t ks3 = (cuuint32_t)(v3->L * v3->KPL);
     alignas(64) CUtensorMap tm;
-    const cuuint64_t gdim[2] = {(cuuint64_t)ks3, (cuuint64_t)V};
+    const cuuint64_t gdim[2] = {(cuuint64_t)ks3 * (ctx->variant3 ? 1 : ctx->variant3c->CL), (cuuint64_t)V};
     const cuuint64_t gstride[1] = {(cuuint64_t)KS * sizeof(double)};
     const cuuint32_t box[2] = {ks3, 1};
     const cuuint32_t estr[2] = {1, 1};
@@ -1206,6 +1251,13 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
   int n_long = (int)ctx->D;
   int cap2 = 0, grid2 = 0;
   size_t smem2 = 0;
+  enum { MAXCLS2 = 2 };
+  struct Class2 {
+    const Estep2Variant *v;
+    int rt, cap, grid, begin, end;
+    size_t smem;
+  } cls2[MAXCLS2];
+  int ncls2 = 0;
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");  // "1": general kernel only (test / profiling aid)
   // the deterministic statistics mode exists in the general kernel only
   const bool use2 = ctx->variant2 && !(fk && atoi(fk) == 1) && !det;
@@ -1229,36 +1281,67 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       if (grid2 > 0) CK(vf->prepare(smem2));
     }
   } else if (use2 && ctx->D > 0) {
-    const Estep2Variant *v2 = ctx->variant2;
-    const int c2 = v2->WPS / v2->NW;
-    const size_t per = std::min(((size_t)233472 - (size_t)c2 * 1024) / c2, ctx->smem_optin) & ~(size_t)15;
-    // slot hierarchy per thread: RREG in registers, then Tensor Memory, then shared memory
+    // classes, longest documents first: the wide cluster variant (cluster variants only), then the
+    // base variant; each takes the documents it holds that the next one does not
+    const char *fcls = getenv("MRLDA_ESTEP2_CLASSES");  // "0": base variant only (profiling aid)
+    const bool wide = !(fcls && atoi(fcls) == 0);
+    const Estep2Variant *cand[MAXCLS2] = {wide ? ctx->variant2_wide : nullptr, ctx->variant2};
     const char *et = getenv("MRLDA_ESTEP2_TMEM");  // "0" disables TMEM slots (profiling aid)
-    const int need_slots = (ctx->max_rows + 31) / 32;
-    int rt = (et && atoi(et) == 0) ? 0 : estep2_tmem_slots(v2->NW, v2->CPW, v2->WPS);
-    rt = std::max(0, std::min(rt, need_slots - v2->RREG));
-    int rsm = 0;
-    while (v2->smem_bytes(rsm + 1, 32 * (v2->RREG + rt + rsm + 1)) <= per) rsm++;
-    rsm = std::max(0, std::min(rsm, need_slots - v2->RREG - rt));
-    cap2 = 32 * (v2->RREG + rt + rsm);
-    a.tmem_slots = rt;
-    if (v2->smem_bytes(rsm, cap2) <= per) {
-      n_long = (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), cap2,
-                                      [](int cap, int32_t nn) { return cap >= nn; }) -
-                     ctx->h_nnz_sorted.begin());
+    for (int k = 0; k < MAXCLS2; k++) {
+      const Estep2Variant *v2 = cand[k];
+      if (!v2) continue;
+      Class2 &c = cls2[ncls2];
+      c.v = v2;
+      const int c2 = v2->WPS / v2->NW;
+      const size_t per = std::min(((size_t)233472 - (size_t)c2 * 1024) / c2, ctx->smem_optin) & ~(size_t)15;
+      // slot hierarchy per thread: RREG in registers, then Tensor Memory, then shared memory
+      int rt = (et && atoi(et) == 0) ? 0 : estep2_tmem_slots(v2->NW, v2->CPW, v2->WPS);
+      int rsm = 0;
+      while (v2->smem_bytes(rsm + 1, 32 * (v2->RREG + rt + rsm + 1)) <= per) rsm++;
+      if (v2->smem_bytes(rsm, 32 * (v2->RREG + rt + rsm)) > per) continue;
+      const int capc = 32 * (v2->RREG + rt + rsm);
+      // first document (descending nnz order) that fits this class
+      c.begin = (int)(std::upper_bound(ctx->h_nnz_sorted.begin(), ctx->h_nnz_sorted.end(), capc,
+                                       [](int cap, int32_t nn) { return cap >= nn; }) -
+                      ctx->h_nnz_sorted.begin());
+      if (ncls2 > 0) c.begin = std::max(c.begin, cls2[ncls2 - 1].begin);
+      ncls2++;
+    }
+    for (int k = 0; k < ncls2; k++) {
+      Class2 &c = cls2[k];
+      const Estep2Variant *v2 = c.v;
+      c.end = k + 1 < ncls2 ? cls2[k + 1].begin : (int)ctx->D;
+      const int c2 = v2->WPS / v2->NW;
+      const size_t per = std::min(((size_t)233472 - (size_t)c2 * 1024) / c2, ctx->smem_optin) & ~(size_t)15;
+      // do not reserve more than the class's longest document needs
+      const int need_slots = c.end > c.begin ? (ctx->h_nnz_sorted[c.begin] + 31) / 32 : 1;
+      int rt = (et && atoi(et) == 0) ? 0 : estep2_tmem_slots(v2->NW, v2->CPW, v2->WPS);
+      rt = std::max(0, std::min(rt, need_slots - v2->RREG));
+      int rsm = 0;
+      while (v2->smem_bytes(rsm + 1, 32 * (v2->RREG + rt + rsm + 1)) <= per) rsm++;
+      rsm = std::max(0, std::min(rsm, need_slots - v2->RREG - rt));
+      c.rt = rt;
+      c.cap = 32 * (v2->RREG + rt + rsm);
       // a cluster variant runs CL CTAs per document; the grid is a whole number of clusters
-      grid2 = v2->CL * (int)std::min<int64_t>((int64_t)c2 * ctx->num_sms / v2->CL, ctx->D - n_long);
+      c.grid = v2->CL * (int)std::min<int64_t>((int64_t)c2 * ctx->num_sms / v2->CL, c.end - c.begin);
       // never let more than c2 CTAs share an SM: they would over-subscribe its 512 TMEM columns
       // and the extra CTA's tcgen05.alloc would wait forever
       const size_t min_dyn = (size_t)233472 / (c2 + 1) - 1024 + 16;
-      smem2 = std::max(v2->smem_bytes(rsm, cap2), std::min(min_dyn, per));
-      if (grid2 > 0) CK(v2->prepare(smem2));
+      c.smem = std::max(v2->smem_bytes(rsm, c.cap), std::min(min_dyn, per));
+      if (c.grid > 0) CK(v2->prepare(c.smem));
+    }
+    if (ncls2 > 0) {
+      n_long = cls2[0].begin;
+      for (int k = 0; k < ncls2; k++) grid2 += cls2[k].grid;
     }
   }
   // Warp-group kernel (estep3): documents are classed by the number of warps they need; class G
   // (G warps per document, 8/G documents in flight per SM) takes the documents of at most
   // G * (R + T + M_G) * RPB rows that do not fit class G/2.  One launch per class, longest first.
-  const Estep3Variant *v3 = (use2f || !use2) ? nullptr : ctx->variant3;
+  const Estep3Variant *v3 = (use2f || !use2) ? nullptr
+                                             : (ctx->variant3 ? ctx->variant3
+                                                              : (ctx->variant3c ? &ctx->variant3c->v : nullptr));
+  const int cl3 = (v3 && !ctx->variant3) ? ctx->variant3c->CL : 1;  // CTAs per document class launch unit
   enum { MAXCLS = 6 };
   int ncls = 0, cls_G[MAXCLS], cls_begin[MAXCLS + 1], cls_M[MAXCLS];
   size_t cls_smem[MAXCLS];
@@ -1289,9 +1372,23 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       if (ci > 0) cls_begin[ci] = std::max(cls_begin[ci], cls_begin[ci - 1]);
     }
     cls_begin[ncls] = (int)ctx->D;
-    if (ok3) {
+    if (ok3 && cl3 == 1) {
       n_long = cls_begin[0];
       grid2 = 0;
+      ncls2 = 0;
+    } else if (ok3) {
+      // cluster warp-group kernel: the documents it does not hold stay with the cluster classes of
+      // the register-stationary kernel (those that hold more rows) and the general kernel
+      grid2 = 0;
+      for (int k = 0; k < ncls2; k++) {
+        Class2 &c2 = cls2[k];
+        c2.begin = std::min(c2.begin, cls_begin[0]);
+        c2.end = std::min(c2.end, cls_begin[0]);
+        const int per_sm = c2.v->WPS / c2.v->NW;
+        c2.grid = c2.v->CL * (int)std::min<int64_t>((int64_t)per_sm * ctx->num_sms / c2.v->CL, c2.end - c2.begin);
+        grid2 += c2.grid;
+      }
+      n_long = ncls2 > 0 ? cls2[0].begin : cls_begin[0];
     } else {
       v3 = nullptr;
     }
@@ -1318,6 +1415,17 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       ctx->launches++;
       if (fork) CK(cudaEventRecord(ctx->ev[7], ctx->stream2));
     }
+    // cluster kernel: the register-stationary cluster classes that hold longer documents go first
+    for (int k = 0; k < ncls2 && cl3 > 1; k++) {
+      const Class2 &cl = cls2[k];
+      if (cl.grid <= 0) continue;
+      a.doc_begin = cl.begin;
+      a.doc_end = cl.end;
+      a.work_counter = ctx->d_work + 10 + k;
+      a.tmem_slots = cl.rt;
+      CK(cl.v->launch(a, cl.grid, cl.cap, cl.smem, st));
+      ctx->launches++;
+    }
     for (int ci = 0; ci < ncls; ci++) {
       const int nd = cls_begin[ci + 1] - cls_begin[ci];
       if (nd <= 0) continue;
@@ -1326,7 +1434,8 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       a.doc_end = cls_begin[ci + 1];
       a.work_counter = ctx->d_work + 4 + ci;
       CK(v3->prepare(cls_smem[ci], G));
-      const int grid = (int)std::min<int64_t>(ctx->num_sms, ((int64_t)nd + per_cta - 1) / per_cta);
+      // launch units: CTAs, or clusters of cl3 CTAs (cluster kernel)
+      const int grid = (int)std::min<int64_t>(ctx->num_sms / cl3, ((int64_t)nd + per_cta - 1) / per_cta);
       CK(v3->launch(a, grid, G, cls_M[ci], cls_smem[ci], st));
       ctx->launches++;
     }
@@ -1354,21 +1463,30 @@ int mrlda_e_step(mrlda_ctx *ctx, mrlda_iter_result *out) {
       CK(det ? ctx->variant->launch_det(a, grid, t, cap, sp) : ctx->variant->launch(a, grid, t, cap, sp));
       ctx->launches++;
     }
-    if (!long_pass && grid2 > 0) {
+    if (!long_pass && grid2 > 0 && use2f) {
       a.doc_begin = n_long;
       a.doc_end = (int)ctx->D;
       a.work_counter = ctx->d_work + 2;
-      cudaError_t e2 = use2f ? ctx->variant2f->launch(a, grid2, cap2, smem2, sp)
-                             : ctx->variant2->launch(a, grid2, cap2, smem2, sp);
-      if (e2 == cudaErrorLaunchOutOfResources && ctx->variant2->CL > 1) {
+      CK(ctx->variant2f->launch(a, grid2, cap2, smem2, sp));
+      ctx->launches++;
+    }
+    for (int k = 0; k < ncls2 && !long_pass && !use2f; k++) {
+      const Class2 &cl = cls2[k];
+      if (cl.grid <= 0) continue;
+      a.doc_begin = cl.begin;
+      a.doc_end = cl.end;
+      a.work_counter = ctx->d_work + 10 + k;
+      a.tmem_slots = cl.rt;
+      cudaError_t e2 = cl.v->launch(a, cl.grid, cl.cap, cl.smem, sp);
+      if (e2 == cudaErrorLaunchOutOfResources && cl.v->CL > 1) {
         // no cluster of this size can be scheduled on this device: the general kernel (still CUDA,
         // never the host) takes these documents as well
         cudaGetLastError();
         plan_estep(ctx, &c, &t, &cap, &smem);
         CK(ctx->variant->prepare(smem));
         a.cap_rows = cap;
-        a.work_counter = ctx->d_work + 3;
-        int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, ctx->D - n_long);
+        a.work_counter = ctx->d_work + 13 + k;
+        int grid = (int)std::min<int64_t>((int64_t)c * ctx->num_sms, cl.end - cl.begin);
         CK(ctx->variant->launch(a, grid, t, cap, sp));
       } else {
         CK(e2);
