@@ -1,0 +1,11 @@
+// estep3c_inst_C2.cu — instantiations of the cluster warp-group E-step kernel (estep3c_kernel.cuh):
+// 2 CTAs of 8 lanes x 26 columns per row, up to 416 topics; per CTA
+// 8 warps x 2 register batches and the Tensor Memory / shared-memory batches of estep3_kernel.cuh.
+#include "estep3c_kernel.cuh"
+
+namespace mrlda {
+const Estep3cVariant g_estep3c_variants_C2[] = {
+    MRLDA_VARIANT3C(8, 26, 2, 8, 2),
+};
+const int g_estep3c_variants_C2_n = sizeof(g_estep3c_variants_C2) / sizeof(g_estep3c_variants_C2[0]);
+}  // namespace mrlda

@@ -1,0 +1,11 @@
+// estep3c_inst_C3.cu — instantiations of the cluster warp-group E-step kernel (estep3c_kernel.cuh):
+// 3 CTAs of 8 lanes x 26 columns per row, up to 624 topics; per CTA
+// 8 warps x 2 register batches and the Tensor Memory / shared-memory batches of estep3_kernel.cuh.
+#include "estep3c_kernel.cuh"
+
+namespace mrlda {
+const Estep3cVariant g_estep3c_variants_C3[] = {
+    MRLDA_VARIANT3C(8, 26, 2, 8, 3),
+};
+const int g_estep3c_variants_C3_n = sizeof(g_estep3c_variants_C3) / sizeof(g_estep3c_variants_C3[0]);
+}  // namespace mrlda

@@ -875,7 +875,21 @@ struct Estep3cVariant {
         CL_                                                                                           \
   }
 
-extern const Estep3cVariant g_estep3c_variants[];
-extern const int g_estep3c_variants_n;
+extern const Estep3cVariant g_estep3c_variants_C2[];
+extern const int g_estep3c_variants_C2_n;
+extern const Estep3cVariant g_estep3c_variants_C2o[];
+extern const int g_estep3c_variants_C2o_n;
+extern const Estep3cVariant g_estep3c_variants_C3[];
+extern const int g_estep3c_variants_C3_n;
+extern const Estep3cVariant g_estep3c_variants_C3o[];
+extern const int g_estep3c_variants_C3o_n;
+extern const Estep3cVariant g_estep3c_variants_C4[];
+extern const int g_estep3c_variants_C4_n;
+extern const Estep3cVariant g_estep3c_variants_C4o[];
+extern const int g_estep3c_variants_C4o_n;
+extern const Estep3cVariant g_estep3c_variants_C5[];
+extern const int g_estep3c_variants_C5_n;
+extern const Estep3cVariant g_estep3c_variants_C5o[];
+extern const int g_estep3c_variants_C5o_n;
 
 }  // namespace mrlda

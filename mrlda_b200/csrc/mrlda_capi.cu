@@ -586,16 +586,19 @@ static const Estep3Variant *select_variant3(int K) {
 static const Estep3cVariant *select_variant3c(int K) {
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");
   if (fk && (atoi(fk) == 1 || atoi(fk) == 2)) return nullptr;
+  const Estep3cVariant *tabs[] = {g_estep3c_variants_C2, g_estep3c_variants_C2o, g_estep3c_variants_C3, g_estep3c_variants_C3o, g_estep3c_variants_C4, g_estep3c_variants_C4o, g_estep3c_variants_C5, g_estep3c_variants_C5o};
+  const int ns[] = {g_estep3c_variants_C2_n, g_estep3c_variants_C2o_n, g_estep3c_variants_C3_n, g_estep3c_variants_C3o_n, g_estep3c_variants_C4_n, g_estep3c_variants_C4o_n, g_estep3c_variants_C5_n, g_estep3c_variants_C5o_n};
   const Estep3cVariant *best = nullptr;
-  for (int i = 0; i < g_estep3c_variants_n; i++) {
-    const Estep3cVariant *v = &g_estep3c_variants[i];
-    const int ks = v->CL * v->v.L * v->v.KPL;
-    // every CTA of the cluster must own at least one topic
-    if (ks < K || (v->CL - 1) * v->v.L * v->v.KPL >= K) continue;
-    if (!best || ks < best->CL * best->v.L * best->v.KPL ||
-        (ks == best->CL * best->v.L * best->v.KPL && v->CL < best->CL))
-      best = v;
-  }
+  for (size_t t = 0; t < sizeof(ns) / sizeof(ns[0]); t++)
+    for (int i = 0; i < ns[t]; i++) {
+      const Estep3cVariant *v = &tabs[t][i];
+      const int ks = v->CL * v->v.L * v->v.KPL;
+      // every CTA of the cluster must own at least one topic
+      if (ks < K || (v->CL - 1) * v->v.L * v->v.KPL >= K) continue;
+      if (!best || ks < best->CL * best->v.L * best->v.KPL ||
+          (ks == best->CL * best->v.L * best->v.KPL && v->CL < best->CL))
+        best = v;
+    }
   return best;
 }
 

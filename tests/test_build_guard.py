@@ -85,6 +85,30 @@ def test_warp_group_kernel_sweeps_do_not_spill(objects, obj):
     assert checked >= 20
 
 
+@pytest.mark.parametrize("obj", ["estep3c_inst_C5o.o", "estep3c_inst_C2.o"])
+def test_cluster_warp_group_kernel_sweeps_do_not_spill(objects, obj):
+    """The same loops with the cross-CTA norm exchange in them (estep3c_kernel.cuh; C5o is cfg 5's
+    K = 1000): still no tile data in local memory."""
+    path = os.path.join(objects, obj)
+    usage = {f: v for f, v in res_usage(path).items() if "estep3c_kernel" in f}
+    assert len(usage) == 4  # G = 1, 2, 4, 8
+    for fn, (reg, stack) in usage.items():
+        assert reg <= 255 and stack <= 64, (fn, reg, stack)
+    checked = 0
+    for fn, ins in sass(path).items():
+        if "estep3c_kernel" not in fn:
+            continue
+        sweeps = [(s, e) for s, e in loops(ins) if 300 < e - s < 3200 and
+                  any("BAR.SYNC" in t for _, t in ins[s:e + 1])]
+        for s, e in sweeps:
+            body = [t for _, t in ins[s:e + 1]]
+            # at most a stray scalar (the exchange counter); never a batch of E
+            assert sum(1 for t in body if re.search(r"\b(LDL|STL)\b", t)) <= 2, (fn, hex(ins[s][0]))
+            assert any("SYNCS" in t or "ST.ASYNC" in t.upper() or "STAS" in t for t in body), (fn, hex(ins[s][0]))
+            checked += 1
+    assert checked >= 20
+
+
 def test_register_stationary_kernel_allocation(objects):
     """estep2_kernel<8,26,2,8,1> (K = 200 when MRLDA_ESTEP_KERNEL=2, and the template of the cluster
     variants): 250-255 registers, no spills, the fast register allocation (the

@@ -219,6 +219,31 @@ def test_sparse_beta_takes_exact_slow_path(capi, oracle, kernel_mode):
     _check(out, ref, c)
 
 
+@pytest.mark.parametrize("K", [300, 1000])
+def test_sparse_beta_slow_path_in_cluster_kernels(capi, oracle, K):
+    """The same situation with the topics split across a thread-block cluster (K > 208): every CTA
+    of the cluster must take the same underflow decisions, read the other CTAs' gamma for the exact
+    redo and add the result to its own topics only.  Documents of 3 to 120 distinct terms."""
+    from mrlda_b200 import corpus
+    V, D = 400, 24
+    rng = np.random.default_rng(5)
+    lb = np.full((V, K), -1.0e12)
+    owner = rng.integers(0, K, size=V)
+    lb[np.arange(V), owner] = np.log(rng.random(V) + 0.1)
+    docs = []
+    for d in range(D):
+        terms = rng.choice(V, size=int(rng.integers(3, 120)), replace=False) + 1
+        docs.append({int(t): int(rng.integers(1, 4)) for t in terms})
+    c = corpus.from_docs(docs, V, K)
+    alpha = np.full(K, 1e-3)
+    g0 = np.full((D, K), 1e-3)
+    g0[:, 0] = 30.0
+    out, ref = _run_pair(capi, oracle, c, alpha, lb, gamma0=g0, sweep_cap=6)
+    assert np.all(np.isfinite(out["gamma"]))
+    assert out["r"]["slow_path_rows"] > 0
+    _check(out, ref, c)
+
+
 def test_three_em_iterations_track_oracle(capi, oracle, kernel_mode):
     """Per-iteration ELBO / logbeta / alpha parity over consecutive iterations (gamma carried)."""
     from mrlda_b200 import corpus
