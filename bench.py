@@ -125,6 +125,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="wikipedia", choices=["ap", "20news", "wikipedia", "largek"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the workload's documents")
+    ap.add_argument("--fit-iterations", type=int, default=0,
+                    help="after the bench: a full fit of this many EM iterations on the same context "
+                         "(tools/r2_fit.py; oracle parity samples on rank 0; not part of the bench line)")
+    ap.add_argument("--fit-sample-at", default="1,25,50")
+    ap.add_argument("--fit-sample-docs", type=int, default=500)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fp32", action="store_true", help="optional fp32 mode (1e-4 tolerance); not the default")
@@ -336,8 +341,6 @@ def main():
                "sample": f"first {n} documents ({ntok} tokens) of the same corpus, {dt:.1f} s, "
                          f"oracle log-space E-step, OpenMP over documents",
                "note": "CPU restatement of Mr.LDA's path (Hadoop LocalJobRunner unavailable: no JVM)"}
-    ctx.close()
-
     if rank == 0:
         hbm, how = _peaks()
         Zmax = max(int(full.row_ptr[b1] - full.row_ptr[b0]) for b0, b1 in
@@ -364,7 +367,11 @@ def main():
                          "peak_source": how,
                          "kernel": "estep3_kernel<8,25,2,8,G>, one launch per document class (G = 8/4/2/1 warps "
                                    "per document), + estep_kernel<8,26> for documents above 320 rows"
-                         if K == 200 else "estep3_kernel / estep2_kernel / estep_kernel",
+                         if K == 200 else
+                                   ("estep3c_kernel<8,25,2,8,G,5> (topics split over a cluster of 5 CTAs), one launch "
+                                    "per document class, + estep2_kernel<8,16,4,8,8> for 321-512 rows + "
+                                    "estep_kernel<32,32> above" if K == 1000
+                                    else "estep3c_kernel / estep2_kernel / estep_kernel"),
                          "algorithmic_bytes_per_launch": B,
                          "note": "binding resource is the FP64 pipe, see fp64"},
             "fp64": {"achieved_tflops": F / (k1_ms_max * 1e-3) / 1e12, "peak_tflops": fp64_peak,
@@ -383,7 +390,22 @@ def main():
                           "ms_per_step": e2e_wall_max * 1e3}
         if cpu:
             out["cpu_baseline"] = cpu
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
+    # ---- optional: a full fit on the same context (saves a second process start on a multi-GPU box) ----
+    if args.fit_iterations > 0:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+        import r2_fit
+        ctx.set_corpus_csr(row_ptr, term_id, count)  # cold gamma again
+        ctx.set_alpha(alpha)
+        ctx.set_logbeta(lb_p)
+        sample_at = sorted({int(x) for x in args.fit_sample_at.split(",") if x and int(x) <= args.fit_iterations})
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):  # stdout carries the one JSON line only
+            rows, parity, fit_wall = r2_fit.run_iterations(ctx, mine, K, rank, args.fit_iterations, sample_at,
+                                                           min(args.fit_sample_docs, mine.n_docs))
+            if rank == 0:
+                r2_fit.write_summary(args.workload, "", world, full, K, V, False, rows, parity, fit_wall, t_gen)
+    ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
