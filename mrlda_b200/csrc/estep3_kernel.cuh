@@ -51,6 +51,7 @@
 #include "estep_kernel.cuh"
 #include "tmem_ops.cuh"
 #include "estep2_kernel.cuh"  // tmem_ld_words / tmem_st_words
+#include "estep3_xchg.cuh"    // cluster variant (estep3c_kernel.cuh): norm exchange between CTAs
 
 namespace mrlda {
 
@@ -227,6 +228,70 @@ static __device__ __noinline__ double estep3_slow_rows(const int32_t *term_id, c
   return lik;
 }
 
+// Exact log-space redo of this warp's underflowed rows (estep3_slow_rows with the topics of the
+// other CTAs read through distributed shared memory; contributions go to this CTA's topics only).
+// Every CTA of the cluster takes the same decisions (identical norms), so the same warp of every CTA
+// is here; they meet on the warp's slow-path mbarrier before anybody's gamma can change.
+template <int L, int KS, int CL>
+static __device__ __noinline__ double estep3c_slow_rows(const int32_t *term_id, const int32_t *count,
+                                                        const double *logbeta, double *stats, int *slow_rows,
+                                                        double *gam_g, double *gextra_g, const int K,
+                                                        const int nb, const unsigned badbits, const int lane,
+                                                        const bool last, const int crank, const uint32_t xbar_u32,
+                                                        unsigned long long *xbar_w) {
+  namespace cg = cooperative_groups;
+  constexpr int RPB = 32 / L;
+  auto gamma_of = [&](int k) -> double { return cg::this_cluster().map_shared_rank(gam_g, k / KS)[k % KS]; };
+  double lik = 0.0;
+  for (int b = 0; b < nb; b++) {
+    unsigned m = __ballot_sync(0xffffffffu, (badbits >> b) & 1u);
+    while (m) {
+      const int gi = (__ffs(m) - 1) / L;
+      m &= ~((L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (gi * L));
+      const int z = b * RPB + gi;
+      const int term = __ldg(term_id + z);
+      const double nw_ = (double)__ldg(count + z);
+      const double *lb = logbeta + (size_t)(term - 1) * K;
+      double mx = -INFINITY;
+      for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gamma_of(k)));
+      mx = warp_max(mx);
+      double sum = 0.0;
+      for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gamma_of(k)) - mx);
+      sum = warp_sum(sum);
+      const double lsum = log(sum);
+      for (int k = lane; k < K; k += 32) {
+        if (k / KS != crank) continue;
+        const double lphi = lb[k] + digamma_fast(gamma_of(k)) - mx - lsum;
+        const double c = nw_ * exp(lphi);
+        if (c > 0.0) {
+          atomicAdd(gextra_g + (k - crank * KS), c);
+          if (last) {
+            lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
+            if (stats) atomicAdd(stats + (size_t)(term - 1) * K + k, c);
+          }
+        }
+      }
+      if (lane == 0 && crank == 0) atomicAdd(slow_rows, 1);
+    }
+  }
+  // rendezvous of the CL warps that read each other's gamma
+  __syncwarp();
+  const uint32_t sb = xbar_u32 + 4u * (uint32_t)sizeof(unsigned long long);
+  if (lane == 0) {
+#pragma unroll
+    for (int d = 1; d < CL; d++) {
+      const int r = crank + d < CL ? crank + d : crank + d - CL;
+      estep3c_arrive_remote(estep3c_mapa(sb, r));
+    }
+  }
+  const uint32_t parity = (uint32_t)xbar_w[5];
+  estep3c_mbar_wait(sb, parity);
+  __syncwarp();
+  if (lane == 0) xbar_w[5] = parity ^ 1u;
+  __syncwarp();
+  return lik;
+}
+
 // Everything a warp needs to walk its batches (built once per kernel).
 template <int L, int KPL, int R, int NW>
 struct Estep3Warp {
@@ -283,11 +348,19 @@ __device__ __forceinline__ void estep3_norm_exchange(const double (&pr)[NA], dou
 // flags in badbits.  The batches are handled as two halves, [0, N1) and [N1, NA): the norm exchange
 // of the first half (shuffles, one reciprocal: a long dependent chain) is in flight behind the dot
 // products of the second half, and the exchange of the second half behind pass B of the first.
-template <int L, int KPL, int R, int NW, int NTM, int NSM>
+//
+// CL > 1 (estep3c_kernel.cuh: the topics are split across a cluster of CL CTAs and this CTA's dot
+// products are partial): the L-lane reduce-scatter of a half leaves lane j with the CTA's partial
+// norm, which goes to the same lane of the same warp in every peer CTA (estep3c_send); both halves
+// are sent as soon as they are known, the warp waits once on its exchange mbarrier and sums the CL
+// partials in rank order.  xc is the warp's exchange counter: buffer and mbarrier xc & 1, mbarrier
+// phase (xc >> 1) & 1.
+template <int L, int KPL, int R, int NW, int NTM, int NSM, int CL = 1>
 __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW> &w,
                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
                                                   const double mycnt1, const double mycnt2, const int lane,
-                                                  double (&s)[KPL], unsigned &badbits, long long (&tm)[8]) {
+                                                  double (&s)[KPL], unsigned &badbits, long long (&tm)[8],
+                                                  const Estep3cX &x, const int xc) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
   constexpr int NA = R + NTM + NSM;  // batches in use; batch i < R + NTM sits in slot i, the others in slot i - NTM + T
@@ -298,6 +371,21 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
   const int j = w.j;
   uint32_t wa[2 * CA], wb[2 * CB];
   badbits = 0;
+  const int par = xc & 1;
+  // first half of the norms: complete them (CL = 1) or send this CTA's partials (CL > 1)
+  auto first_half = [&]() {
+    if constexpr (CL == 1) {
+      estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
+    } else {
+      const double p1 = estep3c_norm_rs<L, NA, 0, N1>(pr, j);
+      if (j < N1) estep3c_send<CL>(x, par, lane, p1);
+    }
+  };
+  if constexpr (CL > 1) {
+    if (lane == 0)
+      estep3c_mbar_expect(x.xbar_u32 + (uint32_t)(par * sizeof(unsigned long long)),
+                          (uint32_t)((CL - 1) * S::RPB * NA * sizeof(double)));
+  }
   // ---- pass A: theta in registers; partial dot products of every batch ----
   {
     double th[KPL];
@@ -315,8 +403,7 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
       }
 #pragma unroll
       for (int q = 0; q < R; q++) pr[q] = (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
-      if constexpr (N1 == R)
-        estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
+      if constexpr (N1 == R) first_half();
     }
 #pragma unroll
     for (int t = 0; t < NTM; t++) {
@@ -331,8 +418,7 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
       for (int c = 0; c < CB; c++)
         ac[c & 3] = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), ac[c & 3]);
       pr[R + t] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
-      if (R + t == N1 - 1 && N1 > R)
-        estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
+      if (R + t == N1 - 1 && N1 > R) first_half();
     }
 #pragma unroll
     for (int m = 0; m < NSM; m++) {
@@ -342,13 +428,27 @@ __device__ __forceinline__ void estep3_sweep_fast(const Estep3Warp<L, KPL, R, NW
 #pragma unroll
       for (int c = 0; c < KPL; c++) ac[c & 3] = fma(th[c], ev[c], ac[c & 3]);
       pr[R + NTM + m] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
-      if (R + NTM + m == N1 - 1 && N1 > R)
-        estep3_norm_exchange<L, NA, 0, N1, R, NTM, T>(pr, rr, mycnt1, j, lane, badbits);
+      if (R + NTM + m == N1 - 1 && N1 > R) first_half();
     }
   }
   MRLDA_TICK_DEP(2, pr[NA - 1]);
   if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // pass B's first load, behind the chains
-  if constexpr (N2 > 0) estep3_norm_exchange<L, NA, N1, (N2 > 0 ? N2 : 1), R, NTM, T>(pr, rr, mycnt2, j, lane, badbits);
+  if constexpr (CL == 1) {
+    if constexpr (N2 > 0)
+      estep3_norm_exchange<L, NA, N1, (N2 > 0 ? N2 : 1), R, NTM, T>(pr, rr, mycnt2, j, lane, badbits);
+  } else {
+    if constexpr (N2 > 0) {
+      const double p2 = estep3c_norm_rs<L, NA, N1, (N2 > 0 ? N2 : 1)>(pr, j);
+      if (j < N2) estep3c_send<CL>(x, par, 32 + lane, p2);
+    }
+    // the peers' partial norms of both halves
+    estep3c_mbar_wait(x.xbar_u32 + (uint32_t)(par * sizeof(unsigned long long)), (uint32_t)((xc >> 1) & 1));
+    const double g1 = j < N1 ? estep3c_total<CL>(x, par, lane) : 1.0;
+    double g2 = 1.0;
+    if constexpr (N2 > 0) g2 = j < N2 ? estep3c_total<CL>(x, par, 32 + lane) : 1.0;
+    estep3c_norm_finish<L, NA, 0, N1, R, NTM, T>(g1, rr, mycnt1, lane, badbits);
+    if constexpr (N2 > 0) estep3c_norm_finish<L, NA, N1, (N2 > 0 ? N2 : 1), R, NTM, T>(g2, rr, mycnt2, lane, badbits);
+  }
   MRLDA_TICK_DEP(3, rr[0]);
   // ---- pass B: S_c += r_w E_wc ----
 #pragma unroll
@@ -550,13 +650,14 @@ __device__ __forceinline__ void estep3_update_gamma(const Estep3Group &q) {
   estep3_update_gamma_pick<L, KPL, G, NC>(q, ncols);
 }
 
-// sweeps 1..I-1 of one document for a warp that holds NTM TMEM and NSM shared-memory batches
-template <int L, int KPL, int R, int NW, int G, int NTM, int NSM>
+// sweeps 1..I-1 of one document for a warp that holds NTM TMEM and NSM shared-memory batches.
+// CL > 1: the sweep counter is the warp's exchange counter (kept in xbar_w[2] between documents).
+template <int L, int KPL, int R, int NW, int G, int NTM, int NSM, int CL = 1>
 __device__ __forceinline__ void estep3_run_sweeps(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
                                                   const Estep3Group &q,
                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
                                                   double *wtot_w, const int nb, const int64_t zrow0,
-                                                  const int lane) {
+                                                  const int lane, const Estep3cX &x, unsigned long long *xbar_w) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int GT = 32 * G, NA = R + NTM + NSM;
   // n_w of the (batch, row) whose norm this lane completes in the two reduce-scatters: batches j and
@@ -567,17 +668,25 @@ __device__ __forceinline__ void estep3_run_sweeps(const EstepArgs &a, const Este
   const int slot2 = b2 < R + NTM ? b2 : b2 - NTM + S::T;
   const double mycnt1 = w.j < N1 ? w.cnt_w[slot1 * S::RPB + w.g] : 0.0;
   const double mycnt2 = b2 < NA ? w.cnt_w[slot2 * S::RPB + w.g] : 0.0;
+  int xc0 = 0;
+  if constexpr (CL > 1) xc0 = (int)xbar_w[2];
   for (int sweep = 0; sweep < a.sweeps - 1; sweep++) {
     double s[KPL];
     unsigned badbits;
     long long tm[8];
     (void)tm;
     MRLDA_TICK(0);
-    estep3_sweep_fast<L, KPL, R, NW, NTM, NSM>(w, e, mycnt1, mycnt2, lane, s, badbits, tm);
+    estep3_sweep_fast<L, KPL, R, NW, NTM, NSM, CL>(w, e, mycnt1, mycnt2, lane, s, badbits, tm, x, xc0 + sweep);
     MRLDA_TICK_DEP(4, s[KPL - 1]);
-    if (__any_sync(0xffffffffu, badbits != 0))
-      (void)estep3_slow_rows<L>(a.term_id + zrow0, a.count + zrow0, a.logbeta, nullptr, a.slow_rows, q.gam_g,
-                                q.gextra_g, q.K, nb, badbits, lane, false);
+    if (__any_sync(0xffffffffu, badbits != 0)) {
+      if constexpr (CL == 1)
+        (void)estep3_slow_rows<L>(a.term_id + zrow0, a.count + zrow0, a.logbeta, nullptr, a.slow_rows, q.gam_g,
+                                  q.gextra_g, q.K, nb, badbits, lane, false);
+      else
+        (void)estep3c_slow_rows<L, S::KS, CL>(a.term_id + zrow0, a.count + zrow0, a.logbeta, nullptr, a.slow_rows,
+                                              q.gam_g, q.gextra_g, a.K, nb, badbits, lane, false, x.crank,
+                                              x.xbar_u32, xbar_w);
+    }
     estep3_publish_s<L, KPL>(s, wtot_w, lane);
     estep3_group_sync(q.bar_id, GT);  // B1: warp sums of S (and slow-path contributions) complete
     MRLDA_TICK(5);
@@ -593,25 +702,30 @@ __device__ __forceinline__ void estep3_run_sweeps(const EstepArgs &a, const Este
     }
 #endif
   }
+  if constexpr (CL > 1) {
+    __syncwarp();
+    if (lane == 0) xbar_w[2] = (unsigned long long)(xc0 + a.sweeps - 1);
+    __syncwarp();
+  }
 }
 
 // picks the specialisation for this warp's batch count (once per document)
-template <int L, int KPL, int R, int NW, int G, int NB_>
+template <int L, int KPL, int R, int NW, int G, int NB_, int CL = 1>
 __device__ __forceinline__ void estep3_dispatch(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
                                                 const Estep3Group &q,
                                                 const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
                                                 double *wtot_w, const int nb, const int64_t zrow0,
-                                                const int lane) {
+                                                const int lane, const Estep3cX &x, unsigned long long *xbar_w) {
   using S = Estep3Shape<L, KPL, R, NW>;
   constexpr int NTM = NB_ > R ? (NB_ - R < S::T ? NB_ - R : S::T) : 0;
   constexpr int NSM = NB_ > R + S::T ? NB_ - R - S::T : 0;
   if constexpr (NB_ >= S::NBMAX) {
-    estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, wtot_w, nb, zrow0, lane);
+    estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM, CL>(a, w, q, e, wtot_w, nb, zrow0, lane, x, xbar_w);
   } else {
     if (nb <= NB_)
-      estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM>(a, w, q, e, wtot_w, nb, zrow0, lane);
+      estep3_run_sweeps<L, KPL, R, NW, G, NTM, NSM, CL>(a, w, q, e, wtot_w, nb, zrow0, lane, x, xbar_w);
     else
-      estep3_dispatch<L, KPL, R, NW, G, NB_ + 1>(a, w, q, e, wtot_w, nb, zrow0, lane);
+      estep3_dispatch<L, KPL, R, NW, G, NB_ + 1, CL>(a, w, q, e, wtot_w, nb, zrow0, lane, x, xbar_w);
   }
 }
 
@@ -765,7 +879,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3_kernel(const EstepArgs a) {
 
     // a warp without rows (short document, more warps than batches) still takes part in the barriers
     // ---- sweeps 1..I-1: loop body specialised on this warp's batch count ----
-    estep3_dispatch<L, KPL, R, NW, G, (R > 1 ? R : 1)>(a, w, q, e, wtot_w, nb, zrow0, lane);
+    estep3_dispatch<L, KPL, R, NW, G, (R > 1 ? R : 1)>(a, w, q, e, wtot_w, nb, zrow0, lane, Estep3cX{}, nullptr);
 
     // ---- last sweep, document epilogue (DocumentMapper.java:244-259,342-346) ----
     {

@@ -29,6 +29,11 @@
 //     likelihood terms) take the same route.
 //   * The last sweep computes all partial norms first, exchanges them once, then runs the fused
 //     likelihood / statistics pass; rank 0 adds the row terms of the likelihood.
+//
+// The sweep loop itself is estep3_kernel.cuh's (estep3_sweep_fast / estep3_run_sweeps /
+// estep3_dispatch instantiated with CL > 1); the exchange primitives are in estep3_xchg.cuh.  This
+// file holds what differs per document: the shared-memory layout, the document loop with its
+// cross-CTA group barrier, the last sweep and the launch glue.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -40,7 +45,7 @@ namespace mrlda {
 template <int L, int KPL, int R, int NW, int CL>
 struct Estep3cSmem {
   using S = Estep3Shape<L, KPL, R, NW>;
-  static constexpr int XSLOTS = 64;  // doubles per (parity, rank) of a warp's exchange buffer
+  static constexpr int XSLOTS = ESTEP3_XSLOTS;  // doubles per (parity, rank) of a warp's exchange buffer
   static_assert(2 * 32 <= XSLOTS && S::NBMAX * S::RPB <= XSLOTS, "exchange buffer too small");
   Estep3Smem<L, KPL, R, NW> base;
   size_t xbuf, xbar, gbar, gsum, total;
@@ -56,40 +61,6 @@ struct Estep3cSmem {
   }
 };
 
-__device__ __forceinline__ uint32_t estep3c_mapa(const uint32_t addr, const int rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-// one double into a peer's shared memory, completing 8 bytes on the peer's mbarrier
-__device__ __forceinline__ void estep3c_st_async(const uint32_t raddr, const double v, const uint32_t rmbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(raddr),
-               "l"(__double_as_longlong(v)), "r"(rmbar)
-               : "memory");
-}
-__device__ __forceinline__ void estep3c_st_remote_i32(const uint32_t raddr, const int v) {
-  asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(raddr), "r"(v) : "memory");
-}
-__device__ __forceinline__ void estep3c_st_remote_f64(const uint32_t raddr, const double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
-}
-__device__ __forceinline__ void estep3c_arrive_remote(const uint32_t rmbar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(rmbar) : "memory");
-}
-__device__ __forceinline__ void estep3c_mbar_wait(const uint32_t mbar, const uint32_t parity) {
-  uint32_t done = 0;
-  while (!done) {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, "
-        "p;\n}"
-        : "=r"(done)
-        : "r"(mbar), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void estep3c_mbar_expect(const uint32_t mbar, const uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
 // TMA gather of four rows, columns [c0, c0 + box) of each
 __device__ __forceinline__ void estep3c_tma_gather4(double *dst, const void *tmap, unsigned long long *mbar,
                                                     const int c0, const int r0, const int r1, const int r2,
@@ -99,318 +70,6 @@ __device__ __forceinline__ void estep3c_tma_gather4(double *dst, const void *tma
       "%4, %5, %6}], [%7];" ::"r"(estep3_smem_u32(dst)),
       "l"(tmap), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(estep3_smem_u32(mbar))
       : "memory");
-}
-
-// What a warp needs for the norm exchange (built once per kernel).
-struct Estep3cX {
-  const double *xbuf_w;  // this warp's exchange buffer [parity][rank][XSLOTS]
-  uint32_t xbuf_u32;     // its shared-memory address
-  uint32_t xbar_u32;     // shared-memory address of this warp's two exchange mbarriers
-  int crank;
-};
-
-// this lane's value to slot `slot` of the exchange buffer of parity `par`: own copy and every peer's
-template <int CL, int XS>
-__device__ __forceinline__ void estep3c_send(const Estep3cX &x, const int par, const int slot, const double v) {
-  const uint32_t la = x.xbuf_u32 + (uint32_t)(((par * CL + x.crank) * XS + slot) * sizeof(double));
-  const uint32_t lm = x.xbar_u32 + (uint32_t)(par * sizeof(unsigned long long));
-  asm volatile("st.shared.f64 [%0], %1;" ::"r"(la), "d"(v) : "memory");
-#pragma unroll
-  for (int d = 1; d < CL; d++) {
-    const int r = x.crank + d < CL ? x.crank + d : x.crank + d - CL;
-    estep3c_st_async(estep3c_mapa(la, r), v, estep3c_mapa(lm, r));
-  }
-}
-// sum over the ranks, in rank order (every CTA gets the same bits)
-template <int CL, int XS>
-__device__ __forceinline__ double estep3c_total(const Estep3cX &x, const int par, const int slot) {
-  const double *p = x.xbuf_w + (size_t)par * CL * XS + slot;
-  double v[CL];
-#pragma unroll
-  for (int r = 0; r < CL; r++) v[r] = p[(size_t)r * XS];
-  double t = v[0];
-#pragma unroll
-  for (int r = 1; r < CL; r++) t += v[r];
-  return t;
-}
-
-// L-lane reduce-scatter of the partial dot products of the batches [START, START + NSV): lane j ends
-// up with this CTA's partial norm of batch START + j, row g (estep3_norm_exchange, first part)
-template <int L, int NA, int START, int NSV>
-__device__ __forceinline__ double estep3c_norm_rs(const double (&pr)[NA], const int j) {
-  static_assert(NSV >= 1 && NSV <= L && START + NSV <= NA, "one batch per lane of a row");
-  double q[L];
-#pragma unroll
-  for (int i = 0; i < L; i++) q[i] = i < NSV ? pr[START + (i < NSV ? i : 0)] : 1.0;
-#pragma unroll
-  for (int o = 1; o < L; o <<= 1) {
-    const bool up = (j & o) != 0;
-#pragma unroll
-    for (int m = 0; m < L / (2 * o); m++) {
-      if (2 * m * o < NSV) {
-        const double send = up ? q[2 * m] : q[2 * m + 1];
-        const double keep = up ? q[2 * m + 1] : q[2 * m];
-        q[m] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-      }
-    }
-  }
-  return q[0];
-}
-// r = n_w / norm_w from the complete norm this lane holds, back to the lanes of the row
-// (estep3_norm_exchange, second part)
-template <int L, int NA, int START, int NSV, int RT, int NTM, int T>
-__device__ __forceinline__ void estep3c_norm_finish(const double nrm, double (&rr)[NA], const double mycnt,
-                                                    const int lane, unsigned &badbits) {
-  const bool live = mycnt > 0.0;
-  const bool ok = nrm >= MRLDA_NORM_TINY;
-  const double r = (live && ok) ? mycnt * rcp_fast(nrm) : 0.0;
-  const int base = lane & ~(L - 1);
-#pragma unroll
-  for (int i = 0; i < NSV; i++) rr[START + i] = __shfl_sync(0xffffffffu, r, base + i);
-  const unsigned bm = __ballot_sync(0xffffffffu, live && !ok);
-  if (bm) {
-    const unsigned mine = bm >> base;
-#pragma unroll
-    for (int i = 0; i < NSV; i++)
-      if ((mine >> i) & 1u) badbits |= 1u << (START + i < RT + NTM ? START + i : START + i - NTM + T);
-  }
-}
-
-// One of the sweeps 1..I-1 (estep3_sweep_fast with the cross-CTA norm exchange).  xc is the warp's
-// exchange counter: buffer and mbarrier xc & 1, mbarrier phase (xc >> 1) & 1.
-template <int L, int KPL, int R, int NW, int CL, int NTM, int NSM>
-__device__ __forceinline__ void estep3c_sweep_fast(const Estep3Warp<L, KPL, R, NW> &w, const Estep3cX &x,
-                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
-                                                   const double mycnt1, const double mycnt2, const int lane,
-                                                   const int xc, double (&s)[KPL], unsigned &badbits) {
-  using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int XS = Estep3cSmem<L, KPL, R, NW, CL>::XSLOTS;
-  constexpr int T = S::T, TW = S::TW, CA = S::CA, CB = S::CB;
-  constexpr int NA = R + NTM + NSM;
-  constexpr int N1 = Estep3Halves<R, NA>::N1, N2 = NA - N1;
-  static_assert(NA > 0 && N1 <= L && N2 <= L, "a warp holds between one and 2 L batches");
-  double pr[NA];
-  double rr[NA];
-  const int j = w.j;
-  const int par = xc & 1;
-  uint32_t wa[2 * CA], wb[2 * CB];
-  badbits = 0;
-  if (lane == 0)
-    estep3c_mbar_expect(x.xbar_u32 + (uint32_t)(par * sizeof(unsigned long long)),
-                        (uint32_t)((CL - 1) * S::RPB * NA * sizeof(double)));
-  // ---- pass A: theta in registers; partial dot products of every batch ----
-  {
-    double th[KPL];
-    estep3_load_cols<L, KPL, false>(w.theta_g, j, th);
-    if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);
-    if constexpr (R > 0) {
-      double acc[S::RA][4];
-#pragma unroll
-      for (int q = 0; q < R; q++) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0;
-#pragma unroll
-      for (int c = 0; c < KPL; c++) {
-#pragma unroll
-        for (int q = 0; q < R; q++) acc[q][c & 3] = fma(th[c], e[q][c], acc[q][c & 3]);
-      }
-#pragma unroll
-      for (int q = 0; q < R; q++) pr[q] = (acc[q][0] + acc[q][1]) + (acc[q][2] + acc[q][3]);
-      if constexpr (N1 == R) {
-        const double p1 = estep3c_norm_rs<L, NA, 0, N1>(pr, j);
-        if (j < N1) estep3c_send<CL, XS>(x, par, lane, p1);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < NTM; t++) {
-      tmem_wait_ld();
-      tmem_ld_words<2 * CB>(w.tbase + (uint32_t)(t * TW + 2 * CA), wb);
-      double ac[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int c = 0; c < CA; c++) ac[c & 3] = fma(th[c], estep3_w2d(wa[2 * c], wa[2 * c + 1]), ac[c & 3]);
-      tmem_wait_ld();
-      if (t + 1 < NTM) tmem_ld_words<2 * CA>(w.tbase + (uint32_t)((t + 1) * TW), wa);
-#pragma unroll
-      for (int c = 0; c < CB; c++)
-        ac[c & 3] = fma(th[CA + c], estep3_w2d(wb[2 * c], wb[2 * c + 1]), ac[c & 3]);
-      pr[R + t] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
-      if (R + t == N1 - 1 && N1 > R) {
-        const double p1 = estep3c_norm_rs<L, NA, 0, N1>(pr, j);
-        if (j < N1) estep3c_send<CL, XS>(x, par, lane, p1);
-      }
-    }
-#pragma unroll
-    for (int m = 0; m < NSM; m++) {
-      double ev[KPL];
-      estep3_tile_ld<L, KPL>(w.tile_w + (size_t)m * 32 * KPL, w.g, j, ev);
-      double ac[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-      for (int c = 0; c < KPL; c++) ac[c & 3] = fma(th[c], ev[c], ac[c & 3]);
-      pr[R + NTM + m] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
-      if (R + NTM + m == N1 - 1 && N1 > R) {
-        const double p1 = estep3c_norm_rs<L, NA, 0, N1>(pr, j);
-        if (j < N1) estep3c_send<CL, XS>(x, par, lane, p1);
-      }
-    }
-  }
-  if constexpr (NTM > 0) tmem_ld_words<2 * CA>(w.tbase, wa);  // pass B's first load, behind the exchange
-  if constexpr (N2 > 0) {
-    const double p2 = estep3c_norm_rs<L, NA, N1, (N2 > 0 ? N2 : 1)>(pr, j);
-    if (j < N2) estep3c_send<CL, XS>(x, par, 32 + lane, p2);
-  }
-  // the peers' partial norms of both halves
-  estep3c_mbar_wait(x.xbar_u32 + (uint32_t)(par * sizeof(unsigned long long)), (uint32_t)((xc >> 1) & 1));
-  {
-    const double g1 = j < N1 ? estep3c_total<CL, XS>(x, par, lane) : 1.0;
-    double g2 = 1.0;
-    if constexpr (N2 > 0) g2 = j < N2 ? estep3c_total<CL, XS>(x, par, 32 + lane) : 1.0;
-    estep3c_norm_finish<L, NA, 0, N1, R, NTM, T>(g1, rr, mycnt1, lane, badbits);
-    if constexpr (N2 > 0) estep3c_norm_finish<L, NA, N1, (N2 > 0 ? N2 : 1), R, NTM, T>(g2, rr, mycnt2, lane, badbits);
-  }
-  // ---- pass B: S_c += r_w E_wc ----
-#pragma unroll
-  for (int c = 0; c < KPL; c++) s[c] = 0.0;
-#pragma unroll
-  for (int q = 0; q < R; q++) {
-#pragma unroll
-    for (int c = 0; c < KPL; c++) s[c] = fma(rr[q], e[q][c], s[c]);
-  }
-#pragma unroll
-  for (int t = 0; t < NTM; t++) {
-    const double r = rr[R + t];
-    tmem_wait_ld();
-    tmem_ld_words<2 * CB>(w.tbase + (uint32_t)(t * TW + 2 * CA), wb);
-#pragma unroll
-    for (int c = 0; c < CA; c++) s[c] = fma(r, estep3_w2d(wa[2 * c], wa[2 * c + 1]), s[c]);
-    tmem_wait_ld();
-    if (t + 1 < NTM) tmem_ld_words<2 * CA>(w.tbase + (uint32_t)((t + 1) * TW), wa);
-#pragma unroll
-    for (int c = 0; c < CB; c++) s[CA + c] = fma(r, estep3_w2d(wb[2 * c], wb[2 * c + 1]), s[CA + c]);
-  }
-#pragma unroll
-  for (int m = 0; m < NSM; m++) {
-    double ev[KPL];
-    estep3_tile_ld<L, KPL>(w.tile_w + (size_t)m * 32 * KPL, w.g, j, ev);
-    const double r = rr[R + NTM + m];
-#pragma unroll
-    for (int c = 0; c < KPL; c++) s[c] = fma(r, ev[c], s[c]);
-  }
-}
-
-// Exact log-space redo of this warp's underflowed rows (estep3_slow_rows with the topics of the
-// other CTAs read through distributed shared memory; contributions go to this CTA's topics only).
-// Every CTA of the cluster takes the same decisions (identical norms), so the same warp of every CTA
-// is here; they meet on the warp's slow-path mbarrier before anybody's gamma can change.
-template <int L, int KS, int CL>
-static __device__ __noinline__ double estep3c_slow_rows(const int32_t *term_id, const int32_t *count,
-                                                        const double *logbeta, double *stats, int *slow_rows,
-                                                        double *gam_g, double *gextra_g, const int K,
-                                                        const int nb, const unsigned badbits, const int lane,
-                                                        const bool last, const int crank, const uint32_t xbar_u32,
-                                                        unsigned long long *xbar_w) {
-  namespace cg = cooperative_groups;
-  constexpr int RPB = 32 / L;
-  auto gamma_of = [&](int k) -> double { return cg::this_cluster().map_shared_rank(gam_g, k / KS)[k % KS]; };
-  double lik = 0.0;
-  for (int b = 0; b < nb; b++) {
-    unsigned m = __ballot_sync(0xffffffffu, (badbits >> b) & 1u);
-    while (m) {
-      const int gi = (__ffs(m) - 1) / L;
-      m &= ~((L == 32 ? 0xffffffffu : ((1u << L) - 1u)) << (gi * L));
-      const int z = b * RPB + gi;
-      const int term = __ldg(term_id + z);
-      const double nw_ = (double)__ldg(count + z);
-      const double *lb = logbeta + (size_t)(term - 1) * K;
-      double mx = -INFINITY;
-      for (int k = lane; k < K; k += 32) mx = fmax(mx, lb[k] + digamma_fast(gamma_of(k)));
-      mx = warp_max(mx);
-      double sum = 0.0;
-      for (int k = lane; k < K; k += 32) sum += exp(lb[k] + digamma_fast(gamma_of(k)) - mx);
-      sum = warp_sum(sum);
-      const double lsum = log(sum);
-      for (int k = lane; k < K; k += 32) {
-        if (k / KS != crank) continue;
-        const double lphi = lb[k] + digamma_fast(gamma_of(k)) - mx - lsum;
-        const double c = nw_ * exp(lphi);
-        if (c > 0.0) {
-          atomicAdd(gextra_g + (k - crank * KS), c);
-          if (last) {
-            lik += c * (lb[k] - lphi);  // DocumentMapper.java:421
-            if (stats) atomicAdd(stats + (size_t)(term - 1) * K + k, c);
-          }
-        }
-      }
-      if (lane == 0 && crank == 0) atomicAdd(slow_rows, 1);
-    }
-  }
-  // rendezvous of the CL warps that read each other's gamma
-  __syncwarp();
-  const uint32_t sb = xbar_u32 + 4u * (uint32_t)sizeof(unsigned long long);
-  if (lane == 0) {
-#pragma unroll
-    for (int d = 1; d < CL; d++) {
-      const int r = crank + d < CL ? crank + d : crank + d - CL;
-      estep3c_arrive_remote(estep3c_mapa(sb, r));
-    }
-  }
-  const uint32_t parity = (uint32_t)xbar_w[5];
-  estep3c_mbar_wait(sb, parity);
-  __syncwarp();
-  if (lane == 0) xbar_w[5] = parity ^ 1u;
-  __syncwarp();
-  return lik;
-}
-
-// sweeps 1..I-1 of one document for a warp that holds NTM TMEM and NSM shared-memory batches
-template <int L, int KPL, int R, int NW, int G, int CL, int NTM, int NSM>
-__device__ __forceinline__ void estep3c_run_sweeps(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
-                                                   const Estep3cX &x, const Estep3Group &q,
-                                                   const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
-                                                   double *wtot_w, unsigned long long *xbar_w, const int nb,
-                                                   const int64_t zrow0, const int lane) {
-  using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int GT = 32 * G, NA = R + NTM + NSM;
-  constexpr int N1 = Estep3Halves<R, NA>::N1;
-  const int b2 = N1 + w.j;
-  const int slot1 = w.j < R + NTM ? w.j : w.j - NTM + S::T;
-  const int slot2 = b2 < R + NTM ? b2 : b2 - NTM + S::T;
-  const double mycnt1 = w.j < N1 ? w.cnt_w[slot1 * S::RPB + w.g] : 0.0;
-  const double mycnt2 = b2 < NA ? w.cnt_w[slot2 * S::RPB + w.g] : 0.0;
-  int xc = (int)xbar_w[2];
-  const int xc_end = xc + a.sweeps - 1;
-  for (; xc < xc_end; xc++) {
-    double s[KPL];
-    unsigned badbits;
-    estep3c_sweep_fast<L, KPL, R, NW, CL, NTM, NSM>(w, x, e, mycnt1, mycnt2, lane, xc, s, badbits);
-    if (__any_sync(0xffffffffu, badbits != 0))
-      (void)estep3c_slow_rows<L, S::KS, CL>(a.term_id + zrow0, a.count + zrow0, a.logbeta, nullptr, a.slow_rows,
-                                            q.gam_g, q.gextra_g, a.K, nb, badbits, lane, false, x.crank,
-                                            x.xbar_u32, xbar_w);
-    estep3_publish_s<L, KPL>(s, wtot_w, lane);
-    estep3_group_sync(q.bar_id, GT);  // B1: warp sums of S (and slow-path contributions) complete
-    estep3_update_gamma<L, KPL, G>(q);
-    estep3_group_sync(q.bar_id, GT);  // B2: theta published
-  }
-  __syncwarp();
-  if (lane == 0) xbar_w[2] = (unsigned long long)xc;
-  __syncwarp();
-}
-
-template <int L, int KPL, int R, int NW, int G, int CL, int NB_>
-__device__ __forceinline__ void estep3c_dispatch(const EstepArgs &a, const Estep3Warp<L, KPL, R, NW> &w,
-                                                 const Estep3cX &x, const Estep3Group &q,
-                                                 const double (&e)[Estep3Shape<L, KPL, R, NW>::RA][KPL],
-                                                 double *wtot_w, unsigned long long *xbar_w, const int nb,
-                                                 const int64_t zrow0, const int lane) {
-  using S = Estep3Shape<L, KPL, R, NW>;
-  constexpr int NTM = NB_ > R ? (NB_ - R < S::T ? NB_ - R : S::T) : 0;
-  constexpr int NSM = NB_ > R + S::T ? NB_ - R - S::T : 0;
-  if constexpr (NB_ >= S::NBMAX) {
-    estep3c_run_sweeps<L, KPL, R, NW, G, CL, NTM, NSM>(a, w, x, q, e, wtot_w, xbar_w, nb, zrow0, lane);
-  } else {
-    if (nb <= NB_)
-      estep3c_run_sweeps<L, KPL, R, NW, G, CL, NTM, NSM>(a, w, x, q, e, wtot_w, xbar_w, nb, zrow0, lane);
-    else
-      estep3c_dispatch<L, KPL, R, NW, G, CL, NB_ + 1>(a, w, x, q, e, wtot_w, xbar_w, nb, zrow0, lane);
-  }
 }
 
 // last sweep, first pass: this CTA's partial norm of the rows of one batch (all L lanes of a row
@@ -716,7 +375,7 @@ __global__ void __launch_bounds__(NW * 32, 1) estep3c_kernel(const EstepArgs a) 
     estep3_group_sync(q.bar_id, GT);
 
     // ---- sweeps 1..I-1: loop body specialised on this warp's batch count ----
-    estep3c_dispatch<L, KPL, R, NW, G, CL, (R > 1 ? R : 1)>(a, w, x, q, e, wtot_w, xbar_w, nb, zrow0, lane);
+    estep3_dispatch<L, KPL, R, NW, G, (R > 1 ? R : 1), CL>(a, w, q, e, wtot_w, nb, zrow0, lane, x, xbar_w);
 
     // ---- last sweep, document epilogue (DocumentMapper.java:244-259,342-346) ----
     {
