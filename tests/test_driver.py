@@ -100,6 +100,9 @@ def test_fresh_training_then_test_mode(tmp_path, oracle):
         ref = oracle.iterate(K, V, held.row_ptr, held.term_id, held.count, lb, a4, learning=False)
         assert abs(tll[0] - ref["log_likelihood"]) <= 1e-9 * abs(ref["log_likelihood"])
     assert not any(f.startswith(("alpha-", "beta-")) for f in os.listdir(tout))  # no model written
+    # the gamma rotation only ever removes gamma-N directories the driver wrote under -output; the
+    # reference's fs.delete(gammaDir) would remove the user's -input here (VI.java:359-379)
+    assert os.path.isfile(tst) and os.path.getsize(tst) > 0
 
 
 def test_informed_prior_option(tmp_path, oracle):
