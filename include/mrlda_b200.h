@@ -188,6 +188,11 @@ int mrlda_debug_phase_cycles(mrlda_ctx *ctx, int64_t out[16]);
 
 /* Number of this library's kernels launched on the context since creation. */
 int64_t mrlda_kernel_launches(const mrlda_ctx *ctx);
+/* Which E-step kernels a context with this many topics uses (fp64 mode), longest documents last, as
+ * one line of text: kernel template instance, cluster size and the largest document (distinct
+ * terms) each holds on a B200.  Pure host code, no CUDA call: answers without a GPU.  Returns the
+ * length written (excluding the terminator), or MRLDA_EINVAL / MRLDA_EUNSUPPORTED. */
+int mrlda_describe_kernels(int n_topics, char *buf, size_t len);
 /* Library/build description, e.g. "mrlda_b200 0.1 sm_100a". */
 const char *mrlda_version(void);
 

@@ -20,7 +20,7 @@ EXPORTS = [
     "mrlda_iterate", "mrlda_e_step", "mrlda_m_step", "mrlda_get_gamma", "mrlda_get_alpha_ss",
     "mrlda_get_stats", "mrlda_update_vector_alpha", "mrlda_update_scalar_alpha",
     "mrlda_eval_special", "mrlda_measure_fp64_peak", "mrlda_debug_phase_cycles", "mrlda_nccl_unique_id", "mrlda_comm_init", "mrlda_kernel_launches",
-    "mrlda_version",
+    "mrlda_version", "mrlda_describe_kernels",
 ]
 
 
@@ -104,6 +104,8 @@ def load():
     L.mrlda_kernel_launches.argtypes = [_ctxp]
     L.mrlda_kernel_launches.restype = C.c_int64
     L.mrlda_version.restype = C.c_char_p
+    L.mrlda_describe_kernels.argtypes = [C.c_int, C.c_char_p, C.c_size_t]
+    L.mrlda_describe_kernels.restype = C.c_int
     _lib = L
     return L
 
@@ -112,6 +114,15 @@ def default_config():
     cfg = MrldaConfig()
     load().mrlda_default_config(C.byref(cfg))
     return cfg
+
+
+def describe_kernels(n_topics):
+    """Which E-step kernels a context with this many topics uses (no GPU needed)."""
+    buf = C.create_string_buffer(1024)
+    rc = load().mrlda_describe_kernels(int(n_topics), buf, len(buf))
+    if rc < 0:
+        raise MrldaError(rc, f"mrlda_describe_kernels({n_topics})")
+    return buf.value.decode()
 
 
 def nccl_unique_id():

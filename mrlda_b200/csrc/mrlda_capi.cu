@@ -568,6 +568,11 @@ static const Estep2Variant *select_cluster_wide(const Estep2Variant *base, int K
 static const Estep3Variant *select_variant3(int K) {
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");
   if (fk && (atoi(fk) == 1 || atoi(fk) == 2)) return nullptr;
+  // up to 104 topics the register-stationary kernel splits its narrower column slices over fewer
+  // warps (several CTAs per SM); a row of the warp-group kernel is 200 or 208 columns wide, so fewer
+  // topics would mostly be padding (MRLDA_ESTEP3_MIN_TOPICS overrides the bound: profiling aid)
+  const char *fm = getenv("MRLDA_ESTEP3_MIN_TOPICS");
+  if (K < (fm ? atoi(fm) : 105)) return nullptr;
   const int want_nw = 8;  // 12- and 16-warp CTAs (no register batches) measured 1.5x / 1.8x slower
   const Estep3Variant *tabs[] = {g_estep3_variants_L8, g_estep3_variants_L8o};
   const int ns[] = {g_estep3_variants_L8_n, g_estep3_variants_L8o_n};
@@ -586,6 +591,10 @@ static const Estep3Variant *select_variant3(int K) {
 static const Estep3cVariant *select_variant3c(int K) {
   const char *fk = getenv("MRLDA_ESTEP_KERNEL");
   if (fk && (atoi(fk) == 1 || atoi(fk) == 2)) return nullptr;
+  // up to 256 topics the register-stationary kernel still holds a document on one SM and beats a
+  // 2-CTA cluster of warp groups (K = 224: 73 against 83 ms, K = 256: 67 against 84 ms per 40 000
+  // documents; from K = 320 on the cluster kernel wins: 84 against 120 ms; tools/kcross_on_box.sh)
+  if (K <= 256) return nullptr;
   const Estep3cVariant *tabs[] = {g_estep3c_variants_C2, g_estep3c_variants_C2o, g_estep3c_variants_C3, g_estep3c_variants_C3o, g_estep3c_variants_C4, g_estep3c_variants_C4o, g_estep3c_variants_C5, g_estep3c_variants_C5o};
   const int ns[] = {g_estep3c_variants_C2_n, g_estep3c_variants_C2o_n, g_estep3c_variants_C3_n, g_estep3c_variants_C3o_n, g_estep3c_variants_C4_n, g_estep3c_variants_C4o_n, g_estep3c_variants_C5_n, g_estep3c_variants_C5o_n};
   const Estep3cVariant *best = nullptr;
@@ -633,6 +642,58 @@ const char *mrlda_last_error(const mrlda_ctx *ctx) {
 }
 
 int64_t mrlda_kernel_launches(const mrlda_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int mrlda_describe_kernels(int n_topics, char *buf, size_t len) {
+  if (!buf || len == 0 || n_topics <= 0) return MRLDA_EINVAL;
+  if (n_topics > MRLDA_MAX_TOPICS) return MRLDA_EUNSUPPORTED;
+  const int K = n_topics;
+  const size_t sm_total = 233472, optin = 232448;  // B200: 228 KB per SM, 227 KB per CTA
+  std::string out;
+  char tmp[256];
+  const Estep3Variant *v3 = select_variant3(K);
+  const Estep3cVariant *v3c = v3 ? nullptr : select_variant3c(K);
+  const Estep2Variant *v2 = select_variant2(K);
+  const Estep2Variant *v2w = select_cluster_wide(v2, K);
+  int held = 0;  // rows the classes so far hold
+  if (v3 || v3c) {
+    const Estep3Variant *v = v3 ? v3 : &v3c->v;
+    const int cl = v3 ? 1 : v3c->CL;
+    const size_t per = std::min(sm_total - 1024, optin) & ~(size_t)15;
+    int M = v->MMAX;
+    while (M > 0 && v->smem_bytes(M, v->NW) > per) M--;
+    held = v->NW * (v->R + v->T + M) * (32 / v->L);
+    snprintf(tmp, sizeof tmp, "%s<%d,%d,%d,%d,G%s> x %d CTA%s per document, G = 1/2/4/8 warps, <= %d rows",
+             v3 ? "estep3_kernel" : "estep3c_kernel", v->L, v->KPL, v->R, v->NW, v3 ? "" : ",CL", cl,
+             cl > 1 ? "s" : "", held);
+    out += tmp;
+  }
+  const Estep2Variant *cand[2] = {v2, (v3c && v2w) ? v2w : nullptr};
+  if (!v3 && !v3c && v2w) cand[1] = v2w;
+  if (v3) cand[0] = cand[1] = nullptr;       // single-CTA warp groups: the general kernel takes the rest
+  if (v3c) cand[0] = nullptr;                // cluster warp groups: only a class that holds more rows
+  for (int k = 0; k < 2; k++) {
+    const Estep2Variant *v = cand[k];
+    if (!v) continue;
+    const int c2 = v->WPS / v->NW;
+    const size_t per = std::min((sm_total - (size_t)c2 * 1024) / c2, optin) & ~(size_t)15;
+    const int rt = estep2_tmem_slots(v->NW, v->CPW, v->WPS);
+    int rsm = 0;
+    while (v->smem_bytes(rsm + 1, 32 * (v->RREG + rt + rsm + 1)) <= per) rsm++;
+    const int cap = 32 * (v->RREG + rt + rsm);
+    if (cap <= held) continue;
+    snprintf(tmp, sizeof tmp, "%sestep2_kernel<%d,%d,%d,%d,%d> x %d CTA%s per document, <= %d rows",
+             out.empty() ? "" : " | ", v->NW, v->CPW, v->RREG, v->WPS, v->CL, v->CL, v->CL > 1 ? "s" : "", cap);
+    out += tmp;
+    held = cap;
+  }
+  const EstepVariant *vg = select_variant(K);
+  if (!vg) return MRLDA_EUNSUPPORTED;
+  snprintf(tmp, sizeof tmp, "%sestep_kernel<%d,%d> longer documents and deterministic mode", out.empty() ? "" : " | ",
+           vg->L, vg->KPL);
+  out += tmp;
+  snprintf(buf, len, "%s", out.c_str());
+  return (int)std::min(out.size(), len - 1);
+}
 
 void mrlda_destroy(mrlda_ctx *ctx) {
   if (!ctx) return;

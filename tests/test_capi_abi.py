@@ -76,3 +76,29 @@ def test_argument_errors_are_codes_not_crashes(capi):
     assert lib.mrlda_iterate(None, None) == -1
     assert lib.mrlda_kernel_launches(None) == 0
     lib.mrlda_destroy(None)
+
+
+def test_kernel_plan_by_topic_count(capi):
+    """mrlda_describe_kernels (pure host code): which E-step kernel family a topic count gets.  The
+    bounds are measured crossovers (tools/kcross_on_box.sh): the
+    register-stationary kernel up to 104 topics and from 209 to 256, single-CTA warp groups from 105 to
+    208, warp groups with the topics split across a cluster above 256."""
+    first = lambda K: capi.describe_kernels(K).split(" | ")[0]
+    for K in (2, 20, 100, 104):
+        assert first(K).startswith("estep2_kernel<") and " x 1 CTA " in first(K), (K, first(K))
+    for K in (105, 160, 200, 208):
+        assert first(K).startswith("estep3_kernel<8,") and "<= " in first(K), (K, first(K))
+    assert first(200).startswith("estep3_kernel<8,25,2,8,G>") and "<= 320 rows" in first(200)
+    for K in (209, 256):
+        assert first(K).startswith("estep2_kernel<8,") and " x 1 CTA " in first(K), (K, first(K))
+    for K, cl in ((257, 2), (400, 2), (513, 3), (800, 4), (1000, 5), (1024, 5)):
+        assert first(K).startswith("estep3c_kernel<8,") and f" x {cl} CTAs " in first(K), (K, first(K))
+    plan = capi.describe_kernels(1000)
+    assert plan.startswith("estep3c_kernel<8,25,2,8,G,CL> x 5 CTAs per document")  # K = 1000 is 5 x 200
+    assert "estep2_kernel<8,16,4,8,8> x 8 CTAs per document, <= 512 rows" in plan
+    assert plan.endswith("estep_kernel<32,32> longer documents and deterministic mode")
+    import pytest
+    with pytest.raises(capi.MrldaError):
+        capi.describe_kernels(0)
+    with pytest.raises(capi.MrldaError):
+        capi.describe_kernels(100000)

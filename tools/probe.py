@@ -19,6 +19,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="wikipedia")
     ap.add_argument("--docs", type=int, default=20000)
+    ap.add_argument("--topics", type=int, default=0, help="override the workload's topic count")
+    ap.add_argument("--terms", type=int, default=0, help="override the workload's vocabulary size")
     ap.add_argument("--min-rows", type=int, default=0)
     ap.add_argument("--max-rows", type=int, default=1 << 30)
     ap.add_argument("--steps", type=int, default=2)
@@ -28,6 +30,8 @@ def main():
     ap.add_argument("--deterministic", action="store_true", help="deterministic statistics mode")
     args = ap.parse_args()
     D0, V, K, mean_len, heavy = corpus.SHAPES[args.workload]
+    K = args.topics or K
+    V = args.terms or V
     c = corpus.generate(args.docs, V, K, mean_len, seed=4, heavy_tail=heavy, device="cuda")
     n = np.diff(c.row_ptr)
     keep = np.nonzero((n >= args.min_rows) & (n <= args.max_rows))[0]
