@@ -887,8 +887,7 @@ static cudaError_t variant2_launch(const EstepArgs &args, int grid, int cap_rows
     if (getenv("MRLDA_DEBUG"))
       fprintf(stderr, "estep2<%d,%d,%d,%d,%d>: grid %d CTAs, smem %zu, cap %d rows, max active clusters %d\n",
               NW, CPW, RREG, WPS, CL, grid, smem, cap_rows, max_clusters);
-    if (grid / CL > max_clusters && !getenv("MRLDA_NO_CLUSTER_CLAMP"))
-      cfg.gridDim = dim3((unsigned)(max_clusters * CL));
+    if (grid / CL > max_clusters) cfg.gridDim = dim3((unsigned)(max_clusters * CL));
     return cudaLaunchKernelEx(&cfg, estep2_kernel<NW, CPW, RREG, WPS, CL>, a);
   }
 }
