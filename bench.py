@@ -365,7 +365,8 @@ def main():
                          "frac": ach / hbm,
                          "traffic": measured_traffic(args.workload, world) if args.scale == 1.0 else None,
                          "peak_source": how,
-                         "kernel": "estep3_kernel<8,25,2,8,G>, one launch per document class (G = 8/4/2/1 warps "
+                         "kernel": "estep2f_kernel (fp32 tile) + estep_kernel (fp64) for longer documents" if args.fp32
+                         else "estep3_kernel<8,25,2,8,G>, one launch per document class (G = 8/4/2/1 warps "
                                    "per document), + estep_kernel<8,26> for documents above 320 rows"
                          if K == 200 else
                                    ("estep3c_kernel<8,25,2,8,G,5> (topics split over a cluster of 5 CTAs), one launch "
@@ -373,7 +374,11 @@ def main():
                                     "estep_kernel<32,32> above" if K == 1000
                                     else "estep3c_kernel / estep2_kernel / estep_kernel"),
                          "algorithmic_bytes_per_launch": B,
-                         "note": "binding resource is the FP64 pipe, see fp64"},
+                         "note": ("optional fp32 mode: estep2f_kernel keeps an fp32 tile on chip, but E rows, gamma "
+                                  "and the statistics stay fp64 in HBM, so the algorithmic bytes are the s = 8 "
+                                  "figure; the fp64 block below is the DFMA fraction of the fp64 formula and does "
+                                  "not describe this mode's FFMA work") if args.fp32
+                         else "binding resource is the FP64 pipe, see fp64"},
             "fp64": {"achieved_tflops": F / (k1_ms_max * 1e-3) / 1e12, "peak_tflops": fp64_peak,
                      "frac": (F / (k1_ms_max * 1e-3) / 1e12) / fp64_peak if fp64_peak else None,
                      "peak_source": "DFMA probe kernel, this run", "algorithmic_flops_per_launch": F},
