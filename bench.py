@@ -366,13 +366,7 @@ def main():
                          "traffic": measured_traffic(args.workload, world) if args.scale == 1.0 else None,
                          "peak_source": how,
                          "kernel": "estep2f_kernel (fp32 tile) + estep_kernel (fp64) for longer documents" if args.fp32
-                         else "estep3_kernel<8,25,2,8,G>, one launch per document class (G = 8/4/2/1 warps "
-                                   "per document), + estep_kernel<8,26> for documents above 320 rows"
-                         if K == 200 else
-                                   ("estep3c_kernel<8,25,2,8,G,5> (topics split over a cluster of 5 CTAs), one launch "
-                                    "per document class, + estep2_kernel<8,16,4,8,8> for 321-512 rows + "
-                                    "estep_kernel<32,32> above" if K == 1000
-                                    else "estep3c_kernel / estep2_kernel / estep_kernel"),
+                         else capi.describe_kernels(K),  # the library's own plan for this topic count
                          "algorithmic_bytes_per_launch": B,
                          "note": ("optional fp32 mode: estep2f_kernel keeps an fp32 tile on chip, but E rows, gamma "
                                   "and the statistics stay fp64 in HBM, so the algorithmic bytes are the s = 8 "
