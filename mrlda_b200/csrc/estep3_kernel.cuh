@@ -990,5 +990,11 @@ extern const Estep3Variant g_estep3_variants_L8[];
 extern const int g_estep3_variants_L8_n;
 extern const Estep3Variant g_estep3_variants_L8o[];
 extern const int g_estep3_variants_L8o_n;
+extern const Estep3Variant g_estep3_variants_L8n17[];
+extern const int g_estep3_variants_L8n17_n;
+extern const Estep3Variant g_estep3_variants_L8n20[];
+extern const int g_estep3_variants_L8n20_n;
+extern const Estep3Variant g_estep3_variants_L8n22[];
+extern const int g_estep3_variants_L8n22_n;
 
 }  // namespace mrlda

@@ -574,8 +574,10 @@ static const Estep3Variant *select_variant3(int K) {
   const char *fm = getenv("MRLDA_ESTEP3_MIN_TOPICS");
   if (K < (fm ? atoi(fm) : 105)) return nullptr;
   const int want_nw = 8;  // 12- and 16-warp CTAs (no register batches) measured 1.5x / 1.8x slower
-  const Estep3Variant *tabs[] = {g_estep3_variants_L8, g_estep3_variants_L8o};
-  const int ns[] = {g_estep3_variants_L8_n, g_estep3_variants_L8o_n};
+  const Estep3Variant *tabs[] = {g_estep3_variants_L8, g_estep3_variants_L8o, g_estep3_variants_L8n17,
+                                 g_estep3_variants_L8n20, g_estep3_variants_L8n22};
+  const int ns[] = {g_estep3_variants_L8_n, g_estep3_variants_L8o_n, g_estep3_variants_L8n17_n,
+                    g_estep3_variants_L8n20_n, g_estep3_variants_L8n22_n};
   const Estep3Variant *best = nullptr;
   for (size_t t = 0; t < sizeof(ns) / sizeof(ns[0]); t++)
     for (int i = 0; i < ns[t]; i++) {

@@ -61,7 +61,8 @@ def is_move(t):
     return "IMAD.MOV" in t or re.match(r"(@!?U?P\d+\s+)?MOV\b", t) is not None
 
 
-@pytest.mark.parametrize("obj", ["estep3_inst_L8o.o", "estep3_inst_L8.o"])
+@pytest.mark.parametrize("obj", ["estep3_inst_L8o.o", "estep3_inst_L8.o", "estep3_inst_L8n17.o", "estep3_inst_L8n20.o",
+                                 "estep3_inst_L8n22.o"])
 def test_warp_group_kernel_sweeps_do_not_spill(objects, obj):
     path = os.path.join(objects, obj)
     usage = {f: v for f, v in res_usage(path).items() if "estep3_kernel" in f}
@@ -80,7 +81,9 @@ def test_warp_group_kernel_sweeps_do_not_spill(objects, obj):
             assert not any(re.search(r"\b(LDL|STL)\b", t) for t in body), (fn, hex(ins[s][0]))
             moves = sum(1 for t in body if is_move(t))
             # ~80 moves of fixed work (constants of exp(digamma), the S exchange) plus a few per batch
-            assert moves <= 60 + 0.10 * len(body), (fn, hex(ins[s][0]), moves, len(body))
+            # (the narrower-row builds for 105..176 topics are not hand-tuned: a little more slack)
+            slack = 60 if obj in ("estep3_inst_L8o.o", "estep3_inst_L8.o") else 80
+            assert moves <= slack + 0.10 * len(body), (fn, hex(ins[s][0]), moves, len(body))
             checked += 1
     assert checked >= 20
 
