@@ -46,3 +46,25 @@ def test_helper_classes_and_patch_are_present():
         old = sum(1 for l in body if l[:1] in (" ", "-") or l == "")
         new = sum(1 for l in body if l[:1] in (" ", "+") or l == "")
         assert (old, new) == (int(m.group(2)), int(m.group(4))), m.group(0)[:80]
+
+
+def test_patch_applies_to_the_reference_driver(tmp_path):
+    """Where the reference tree is present (this container, not the GPU box) the patch must apply
+    to the unmodified cc.mrlda.VariationalInference with no fuzz and no rejected hunk."""
+    import shutil
+
+    import pytest
+    ref = "/root/reference/src/main/java/cc/mrlda/VariationalInference.java"
+    if not os.path.exists(ref) or shutil.which("patch") is None:
+        pytest.skip("reference tree or patch(1) not available")
+    dst = tmp_path / "src" / "main" / "java" / "cc" / "mrlda"
+    dst.mkdir(parents=True)
+    shutil.copy(ref, dst / "VariationalInference.java")
+    r = subprocess.run(["patch", "-p1", "--fuzz=0", "-i", os.path.join(ROOT, "java", "VariationalInference.patch")],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0 and "FAILED" not in r.stdout and "fuzz" not in r.stdout, r.stdout + r.stderr
+    patched = (dst / "VariationalInference.java").read_text()
+    original = open(ref).read()  # (its own brace count is off by one: a brace in a string literal)
+    assert "MrLdaB200" in patched
+    assert patched.count("{") - patched.count("}") == original.count("{") - original.count("}")
+    assert not list(tmp_path.rglob("*.rej"))
