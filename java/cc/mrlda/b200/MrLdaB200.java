@@ -9,7 +9,10 @@ import java.io.IOException;
  * (VariationalInference.java:237-256): the caller hands over the input split, alpha and beta,
  * calls {@link #iterate()} once per EM iteration and reads back the next alpha / beta / gamma and
  * the counters. Every native method is one call of the C ABI (java/jni/mrlda_b200_jni.c); arrays
- * are borrowed for the duration of the call and copied by the library.
+ * are borrowed for the duration of the call and copied by the library. The glue checks every array
+ * length against K, V, D and Z before the call and throws IOException on a mismatch. Java arrays
+ * hold at most 2^31 - 1 elements, so one instance takes D * K and V * K below that (cfg 5: 2M
+ * documents x 1000 topics over 8 ranks = 2.5e8 per rank).
  */
 public final class MrLdaB200 implements AutoCloseable {
   static {
@@ -20,8 +23,9 @@ public final class MrLdaB200 implements AutoCloseable {
   public static final int LL_COUNTER = 0, N_DOCS = 1, N_TERMS_SEEN = 2, N_TOKENS = 3;
 
   private long handle; // mrlda_ctx*, 0 after close()
-  private final int topics;
-  private final int terms;
+  private final int topics; // K, read by the JNI glue to check array lengths
+  private final int terms; // V
+  private long docs; // D of the last successful setCorpus (set by the glue)
 
   /**
    * mrlda_create. The booleans are the JobConf keys VariationalInference sets per iteration
@@ -41,6 +45,11 @@ public final class MrLdaB200 implements AutoCloseable {
 
   public int getNumberOfTerms() {
     return terms;
+  }
+
+  /** D of the corpus loaded by the last successful {@link #setCorpus}. */
+  public long getNumberOfDocuments() {
+    return docs;
   }
 
   /**

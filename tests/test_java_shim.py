@@ -68,3 +68,38 @@ def test_patch_applies_to_the_reference_driver(tmp_path):
     assert "MrLdaB200" in patched
     assert patched.count("{") - patched.count("}") == original.count("{") - original.count("}")
     assert not list(tmp_path.rglob("*.rej"))
+
+
+def _glue_functions():
+    glue = open(GLUE).read()
+    parts = re.split(r"^JNIEXPORT ", glue, flags=re.M)[1:]
+    return {re.search(r"MrLdaB200_(\w+)\s*\(", p).group(1): p for p in parts}
+
+
+def test_glue_checks_array_lengths_before_the_abi_call():
+    """The C ABI trusts pointer extents; a short Java array must become an IOException in the glue."""
+    fns = _glue_functions()
+    for name in ("setCorpus", "setAlpha", "setBeta", "getBeta", "getGamma"):
+        body = fns[name]
+        assert "bad_length(" in body, name
+        call = re.search(r"\bmrlda_(?:set|get)_\w+\(ctx", body)
+        assert call and body.index("bad_length(") < call.start(), name  # checked before the ABI call
+    assert "rowPtr[D]" in fns["setCorpus"]  # termId / count against Z
+
+
+def test_glue_calls_no_jni_function_inside_a_critical_region():
+    """Between GetPrimitiveArrayCritical and the last Release no other JNI call is allowed (JNI
+    specification); throw_io / check / set_docs call JNI and must come after the last unpin."""
+    for name, body in _glue_functions().items():
+        if "pin(env" not in body:
+            continue
+        first = body.index("pin(env")
+        last = body.rindex("unpin(env")
+        region = body[first:last]
+        for banned in ("throw_io(", "check(env", "set_docs(", "GetArrayLength", "_of(env"):
+            # a pin that fails on the FIRST array holds nothing yet; that early exit is the only allowed one
+            hits = [m.start() for m in re.finditer(re.escape(banned), region)]
+            for h in hits:
+                before = region[:h]
+                assert before.count("pin(env") - before.count("unpin(env") == 1 and "kPinFailed" in region[h:h + 40], \
+                    (name, banned)
