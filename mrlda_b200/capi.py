@@ -183,11 +183,19 @@ class Context:
         self._ck(load().mrlda_comm_init(self._h, buf))
 
     def set_corpus_csr(self, row_ptr, term_id, count, doc_id=None, gamma0=None):
-        row_ptr = _arr(row_ptr, np.int64)
-        term_id = _arr(term_id, np.int32)
-        count = _arr(count, np.int32)
-        D = len(row_ptr) - 1
+        # the ABI takes plain pointers and trusts their extents: check every length here
+        row_ptr = _arr(row_ptr, np.int64).ravel()
+        term_id = _arr(term_id, np.int32).ravel()
+        count = _arr(count, np.int32).ravel()
+        if row_ptr.size < 1:
+            raise ValueError("row_ptr must hold D+1 values")
+        D = row_ptr.size - 1
+        Z = int(row_ptr[D])
+        if Z < 0 or term_id.size < Z or count.size < Z:
+            raise ValueError("term_id / count are shorter than row_ptr[D]")
         did = _arr(doc_id, np.int32) if doc_id is not None else None
+        if did is not None and did.size != D:
+            raise ValueError("doc_id must hold D values")
         g0 = _arr(gamma0, np.float64) if gamma0 is not None else None
         if g0 is not None and g0.size != D * self.K:
             raise ValueError("gamma0 must hold D*K values")
@@ -241,8 +249,10 @@ class Context:
 
     def set_informed_prior(self, topics, terms):
         """(topic, term) seed pairs, both 1-based; empty lists remove the prior."""
-        t = _arr(topics, np.int32)
-        v = _arr(terms, np.int32)
+        t = _arr(topics, np.int32).ravel()
+        v = _arr(terms, np.int32).ravel()
+        if t.size != v.size:
+            raise ValueError("topics and terms must have the same length")
         self._ck(load().mrlda_set_informed_prior(self._h, len(t), t.ctypes.data_as(_ip),
                                                  v.ctypes.data_as(_ip)))
 
@@ -263,6 +273,9 @@ class Context:
 
     def get_gamma(self, out=None):
         g = out if out is not None else np.empty((self.D, self.K), dtype=np.float64)
+        if (not isinstance(g, np.ndarray) or g.dtype != np.float64 or not g.flags.c_contiguous
+                or not g.flags.writeable or g.size != self.D * self.K):
+            raise ValueError("out must be a writable C-contiguous float64 array of D*K values")
         self._ck(load().mrlda_get_gamma(self._h, g.ctypes.data_as(_dp)))
         return g
 
@@ -279,6 +292,8 @@ class Context:
     def update_vector_alpha(self, K, n_docs, alpha, ss):
         a = _arr(alpha, np.float64)
         s = _arr(ss, np.float64)
+        if K < 1 or a.size != K or s.size != K:
+            raise ValueError("alpha and ss must hold K values")
         out = np.empty(K, dtype=np.float64)
         self._ck(load().mrlda_update_vector_alpha(self._h, K, n_docs, a.ctypes.data_as(_dp),
                                                   s.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))

@@ -102,3 +102,38 @@ def test_kernel_plan_by_topic_count(capi):
         capi.describe_kernels(0)
     with pytest.raises(capi.MrldaError):
         capi.describe_kernels(100000)
+
+
+def test_binding_checks_buffer_extents_before_the_call(capi):
+    """The ABI takes plain pointers and trusts their extents, so the ctypes binding refuses short or
+    ill-typed buffers itself (ValueError) before any pointer reaches the library.  Runs without a
+    GPU: the checks come before the C call, on a Context that owns no handle."""
+    import numpy as np
+    import pytest
+    ctx = capi.Context.__new__(capi.Context)
+    ctx.K, ctx.V, ctx.D, ctx._h = 3, 5, 2, None
+    rp = np.array([0, 2, 3], dtype=np.int64)
+    with pytest.raises(ValueError, match="row_ptr"):
+        ctx.set_corpus_csr(np.zeros(0, np.int64), [], [])
+    with pytest.raises(ValueError, match="shorter"):
+        ctx.set_corpus_csr(rp, [1, 2], [1, 1, 1])
+    with pytest.raises(ValueError, match="shorter"):
+        ctx.set_corpus_csr(rp, [1, 2, 3], [1, 1])
+    with pytest.raises(ValueError, match="doc_id"):
+        ctx.set_corpus_csr(rp, [1, 2, 3], [1, 1, 1], doc_id=[7])
+    with pytest.raises(ValueError, match="gamma0"):
+        ctx.set_corpus_csr(rp, [1, 2, 3], [1, 1, 1], gamma0=np.ones(5))
+    with pytest.raises(ValueError):
+        ctx.set_alpha(np.ones(2))
+    with pytest.raises(ValueError):
+        ctx.set_logbeta(np.zeros((5, 2)))
+    with pytest.raises(ValueError):
+        ctx.set_beta(np.zeros((5, 3)), np.zeros(3, np.float32), np.zeros(4, np.uint8))
+    with pytest.raises(ValueError, match="same length"):
+        ctx.set_informed_prior([1, 2], [1])
+    for bad in (np.empty((2, 2)), np.empty((2, 3), np.float32), np.empty((3, 2)).T, [0.0] * 6):
+        with pytest.raises(ValueError, match="out must be"):
+            ctx.get_gamma(out=bad)
+    with pytest.raises(ValueError):
+        ctx.update_vector_alpha(3, 10, np.ones(3), np.ones(2))
+    ctx._h = capi._ctxp()  # so that __del__ finds nothing to destroy
