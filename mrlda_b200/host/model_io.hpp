@@ -3,11 +3,16 @@
 // validity checks (Preconditions.checkArgument -> std::invalid_argument).
 #pragma once
 #include <dirent.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
+#include <cstdlib>
+#include <exception>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "seqfile.hpp"
@@ -51,52 +56,216 @@ inline std::vector<std::string> input_files(const std::string &path) {
   return out;
 }
 
-// SequenceFile<IntWritable, cc.mrlda.Document> -> CSR.  Entry order within a document is the
-// writer's HMapII iteration order (arbitrary); it is kept as found.  Only the documents with
-// global index in [first, last) are kept (the others are skipped without being parsed).
-inline Corpus read_corpus(const std::string &path, int n_topics, int n_terms, int64_t first = 0,
-                          int64_t last = INT64_MAX) {
-  Corpus c;
-  bool all_gamma = true;
-  int64_t index = 0;
-  for (const std::string &file : input_files(path)) {
-    if (index >= last) break;
-    SeqReader r(file);
-    if (r.key_class != kIntWritable || r.value_class != kDocument)
-      throw std::invalid_argument(file + ": expected <" + kIntWritable + ", " + kDocument + ">, found <" +
-                                  r.key_class + ", " + r.value_class + ">");
-    const uint8_t *k, *v;
-    size_t kl, vl;
-    Document doc;
-    while (index < last && r.next(k, kl, v, vl)) {
-      if (index++ < first) continue;
-      ByteReader kr(k, kl), vr(v, vl);
-      c.doc_id.push_back(kr.i32());
-      doc.read(vr);
-      for (auto &e : doc.content) {
-        if (e.first < 1 || e.first > n_terms)
-          throw std::invalid_argument("term id " + std::to_string(e.first) + " outside [1," +
-                                      std::to_string(n_terms) + "] in document " +
-                                      std::to_string(c.doc_id.back()));
-        c.term_id.push_back(e.first);
-        c.count.push_back(e.second);
+// How many host threads the file readers / writers may use (part files are independent streams).
+inline int io_threads(size_t jobs) {
+  unsigned hw = std::thread::hardware_concurrency();
+  if (const char *e = getenv("MRLDA_IO_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  return (int)std::max<size_t>(1, std::min<size_t>({jobs, (size_t)std::max(1u, hw), (size_t)16}));
+}
+
+// Runs job(0..n-1) on up to io_threads(n) threads; the first failure (in job order) is rethrown.
+template <class F>
+inline void parallel_jobs(size_t n, F job) {
+  const int T = io_threads(n);
+  if (T <= 1) {
+    for (size_t i = 0; i < n; i++) job(i);
+    return;
+  }
+  std::vector<std::exception_ptr> err(n);
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < T; t++)
+    pool.emplace_back([&] {
+      for (size_t i; (i = next.fetch_add(1)) < n;) {
+        try {
+          job(i);
+        } catch (...) {
+          err[i] = std::current_exception();
+        }
       }
-      c.row_ptr.push_back((int64_t)c.term_id.size());
-      if ((int)doc.gamma.size() == n_topics && all_gamma)
-        c.gamma.insert(c.gamma.end(), doc.gamma.begin(), doc.gamma.end());
-      else
-        all_gamma = false;  // DocumentMapper.java:184: a stored gamma of another length is ignored
+    });
+  for (auto &th : pool) th.join();
+  for (auto &e : err)
+    if (e) std::rethrow_exception(e);
+}
+
+// Big arrays are sized once and backed by transparent huge pages where the kernel offers them on
+// request: first-touch page faults of 4 KB pages are serialised per process and would otherwise
+// bound the reader (0.12 s per 256 MB here, against 0.04 s with 2 MB pages).
+template <class T>
+inline void alloc_huge(std::vector<T> &v, size_t n) {
+  v.reserve(n);
+#ifdef MADV_HUGEPAGE
+  const size_t bytes = v.capacity() * sizeof(T), two_mb = (size_t)2 << 20;
+  if (bytes >= 4 * two_mb) {
+    const uintptr_t lo = ((uintptr_t)v.data() + two_mb - 1) & ~(uintptr_t)(two_mb - 1);
+    const uintptr_t hi = ((uintptr_t)v.data() + bytes) & ~(uintptr_t)(two_mb - 1);
+    if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);  // a hint: failure is harmless
+  }
+#endif
+  v.resize(n);
+}
+
+// First pass over one part file: per record the entry count at the head of the Document value and
+// whether the record carries a gamma of exactly n_topics values.
+struct FileScan {
+  std::vector<int32_t> entries;
+  std::vector<uint8_t> k_gamma;
+};
+inline void check_document_file(const SeqReader &r, const std::string &file) {
+  if (r.key_class != kIntWritable || r.value_class != kDocument)
+    throw std::invalid_argument(file + ": expected <" + kIntWritable + ", " + kDocument + ">, found <" +
+                                r.key_class + ", " + r.value_class + ">");
+}
+inline FileScan scan_corpus_file(const std::string &file, int n_topics) {
+  SeqReader r(file);
+  check_document_file(r, file);
+  FileScan s;
+  const uint8_t *k, *v;
+  size_t kl, vl;
+  while (r.next(k, kl, v, vl)) {
+    ByteReader vr(v, vl);
+    const int32_t n = vr.i32();
+    if (n > 0) {
+      vr.need((size_t)n * 8);
+      vr.p += (size_t)n * 8;
+    }
+    const int32_t kk = vr.i32();
+    s.entries.push_back(n > 0 ? n : 0);
+    s.k_gamma.push_back(kk == n_topics && kk > 0 ? 1 : 0);
+  }
+  return s;
+}
+
+// Second pass over one part file: the records with file-local index in [skip, skip + keep) are
+// parsed straight into the final arrays — document i of them at row doc_base + i, its entries from
+// entry_base on.  Entry order within a document is the writer's HMapII iteration order (arbitrary)
+// and is kept as found; a repeated term id keeps its first position and the last count
+// (HMapII.put), which leaves the file's entries short of the scanned count: the number actually
+// written is returned and the caller closes the gap.  gamma (may be null) receives D x K values.
+inline int64_t parse_corpus_file(const std::string &file, const FileScan &scan, int n_topics, int n_terms,
+                                 int64_t skip, int64_t keep, int64_t doc_base, int64_t entry_base,
+                                 Corpus &c, double *gamma) {
+  SeqReader r(file);
+  check_document_file(r, file);
+  const uint8_t *k, *v;
+  size_t kl, vl;
+  TermSlots slots;
+  int64_t at = entry_base;
+  for (int64_t rec = 0; rec < skip + keep; rec++) {
+    if (!r.next(k, kl, v, vl)) throw std::runtime_error(file + ": changed while it was being read");
+    if (rec < skip) continue;
+    const int64_t d = doc_base + (rec - skip);
+    ByteReader kr(k, kl), vr(v, vl);
+    const int32_t doc = kr.i32();
+    c.doc_id[(size_t)d] = doc;
+    const int32_t n = vr.i32();
+    if ((n > 0 ? n : 0) != scan.entries[(size_t)rec])
+      throw std::runtime_error(file + ": changed while it was being read");
+    if (n > 0) {  // numEntries <= 0  =>  content = null
+      vr.need((size_t)n * 8);
+      slots.begin((size_t)n);
+      for (int32_t i = 0; i < n; i++) {
+        const int32_t id = ByteReader::get32(vr.p), cnt = ByteReader::get32(vr.p + 4);
+        vr.p += 8;
+        if (id < 1 || id > n_terms)
+          throw std::invalid_argument("term id " + std::to_string(id) + " outside [1," +
+                                      std::to_string(n_terms) + "] in document " + std::to_string(doc));
+        const int64_t seen = slots.find_or_add(id, at);
+        if (seen < 0) {
+          c.term_id[(size_t)at] = id;
+          c.count[(size_t)at] = cnt;
+          at++;
+        } else {
+          c.count[(size_t)seen] = cnt;
+        }
+      }
+    }
+    c.row_ptr[(size_t)d + 1] = at;
+    if (gamma) {
+      const int32_t kk = vr.i32();
+      if (kk != n_topics) throw std::runtime_error(file + ": changed while it was being read");
+      vr.need((size_t)kk * 8);
+      double *g = gamma + (size_t)d * (size_t)n_topics;
+      for (int32_t i = 0; i < kk; i++) {
+        const int64_t bits = ByteReader::get64(vr.p + (size_t)i * 8);
+        memcpy(&g[i], &bits, 8);
+      }
     }
   }
-  if (!all_gamma) c.gamma.clear();
+  return at - entry_base;
+}
+
+// SequenceFile<IntWritable, cc.mrlda.Document> directory -> CSR: the documents with global index in
+// [first, last), in part-file name order.  Two passes, each taking the part files concurrently: the
+// first reads the entry count of every record (`scans`, when the caller has done that already),
+// which fixes every array size and every part file's place in them; the second parses each file's
+// records straight into place.  Gamma is kept only when every kept document carries a vector of
+// n_topics values (DocumentMapper.java:184: a stored gamma of another length is ignored).
+inline Corpus read_corpus(const std::string &path, int n_topics, int n_terms, int64_t first = 0,
+                          int64_t last = INT64_MAX, const std::vector<FileScan> *scans = nullptr) {
+  const std::vector<std::string> files = input_files(path);
+  std::vector<FileScan> own;
+  if (!scans || scans->size() != files.size()) {
+    own.resize(files.size());
+    parallel_jobs(files.size(), [&](size_t f) { own[f] = scan_corpus_file(files[f], n_topics); });
+    scans = &own;
+  }
+  const size_t F = files.size();
+  std::vector<int64_t> skip(F, 0), keep(F, 0), doc_base(F, 0), entry_base(F, 0), counted(F, 0);
+  int64_t index = 0, D = 0, Z = 0;
+  bool all_gamma = true;
+  if (first < 0) first = 0;
+  for (size_t f = 0; f < F; f++) {
+    const FileScan &s = (*scans)[f];
+    const int64_t n = (int64_t)s.entries.size();
+    const int64_t a = std::min(std::max(first - index, (int64_t)0), n);
+    const int64_t b = std::min(std::max(last - index, (int64_t)0), n);
+    skip[f] = a;
+    keep[f] = std::max(b - a, (int64_t)0);
+    doc_base[f] = D;
+    entry_base[f] = Z;
+    for (int64_t i = a; i < a + keep[f]; i++) {
+      counted[f] += s.entries[(size_t)i];
+      if (!s.k_gamma[(size_t)i]) all_gamma = false;
+    }
+    D += keep[f];
+    Z += counted[f];
+    index += n;
+  }
+  Corpus c;
+  alloc_huge(c.row_ptr, (size_t)D + 1);
+  alloc_huge(c.doc_id, (size_t)D);
+  alloc_huge(c.term_id, (size_t)Z);
+  alloc_huge(c.count, (size_t)Z);
+  if (all_gamma && D > 0) alloc_huge(c.gamma, (size_t)D * (size_t)n_topics);
+  c.row_ptr[0] = 0;
+  std::vector<int64_t> used(F, 0);
+  parallel_jobs(F, [&](size_t f) {
+    if (keep[f] == 0) return;
+    used[f] = parse_corpus_file(files[f], (*scans)[f], n_topics, n_terms, skip[f], keep[f], doc_base[f],
+                                entry_base[f], c, c.gamma.empty() ? nullptr : c.gamma.data());
+  });
+  // repeated term ids inside a record left a file short of its scanned entry count: close the gaps
+  int64_t gap = 0;
+  for (size_t f = 0; f < F; f++) {
+    if (gap > 0 && keep[f] > 0) {
+      memmove(&c.term_id[(size_t)(entry_base[f] - gap)], &c.term_id[(size_t)entry_base[f]], (size_t)used[f] * 4);
+      memmove(&c.count[(size_t)(entry_base[f] - gap)], &c.count[(size_t)entry_base[f]], (size_t)used[f] * 4);
+      for (int64_t d = doc_base[f]; d < doc_base[f] + keep[f]; d++) c.row_ptr[(size_t)d + 1] -= gap;
+    }
+    gap += counted[f] - used[f];
+  }
+  c.term_id.resize((size_t)(Z - gap));
+  c.count.resize((size_t)(Z - gap));
   return c;
 }
 
-// The input split of one rank (the map phase's input splits): a first streaming pass reads only
-// the entry count at the head of every Document value and cuts the document range into `world`
-// contiguous pieces balanced by entries, as corpus.shard_bounds does; the second pass parses this
-// rank's piece alone, so no rank ever holds more than its own shard.  first_doc receives the
-// global index of the shard's first document.
+// The input split of one rank (the map phase's input splits): the first pass (entry counts of every
+// record, part files taken concurrently) cuts the document range into `world` contiguous pieces
+// balanced by entries, as corpus.shard_bounds does; the second pass parses this rank's piece alone,
+// so no rank ever holds more than its own shard.  first_doc receives the global index of the
+// shard's first document.
 inline Corpus read_corpus_shard(const std::string &path, int n_topics, int n_terms, int rank, int world,
                                 int64_t *first_doc = nullptr, int64_t *total_docs = nullptr) {
   if (world <= 1) {
@@ -105,20 +274,12 @@ inline Corpus read_corpus_shard(const std::string &path, int n_topics, int n_ter
     if (total_docs) *total_docs = c.n_docs();
     return c;
   }
+  const std::vector<std::string> files = input_files(path);
+  std::vector<FileScan> scans(files.size());
+  parallel_jobs(files.size(), [&](size_t f) { scans[f] = scan_corpus_file(files[f], n_topics); });
   std::vector<int64_t> rp{0};
-  for (const std::string &file : input_files(path)) {
-    SeqReader r(file);
-    if (r.key_class != kIntWritable || r.value_class != kDocument)
-      throw std::invalid_argument(file + ": expected <" + kIntWritable + ", " + kDocument + ">, found <" +
-                                  r.key_class + ", " + r.value_class + ">");
-    const uint8_t *k, *v;
-    size_t kl, vl;
-    while (r.next(k, kl, v, vl)) {
-      ByteReader vr(v, vl);
-      const int32_t n = vr.i32();
-      rp.push_back(rp.back() + (n > 0 ? n : 0));
-    }
-  }
+  for (auto &s : scans)
+    for (int32_t n : s.entries) rp.push_back(rp.back() + n);
   const int64_t D = (int64_t)rp.size() - 1, Z = rp.back();
   auto bound = [&](int r) -> int64_t {
     if (r <= 0) return 0;
@@ -129,7 +290,7 @@ inline Corpus read_corpus_shard(const std::string &path, int n_topics, int n_ter
   const int64_t hi = std::min(std::max(bound(rank + 1), lo), D);
   if (first_doc) *first_doc = lo;
   if (total_docs) *total_docs = D;
-  return read_corpus(path, n_topics, n_terms, lo, hi);
+  return read_corpus(path, n_topics, n_terms, lo, hi, &scans);
 }
 
 // exportAlpha (VariationalInference.java:549-558)
@@ -141,6 +302,7 @@ inline void write_alpha(const std::string &path, const std::vector<double> &alph
     v.f64(alpha[i]);
     w.append(k, v);
   }
+  w.close();
 }
 
 // importAlpha (VariationalInference.java:521-540)
@@ -183,6 +345,7 @@ inline void write_beta(const std::string &path, int K, int V, const double *dl, 
       }
     w.append(key, val);
   }
+  w.close();
 }
 
 // importBeta's parse (DocumentMapper.java:475-536) into the arrays mrlda_set_beta takes.
@@ -226,18 +389,72 @@ inline void read_beta(const std::string &path, int K, int V, std::vector<double>
 inline void write_gamma(const std::string &file, const Corpus &c, int64_t lo, int64_t hi,
                         const double *gamma /* (hi-lo) x K */, int K) {
   SeqWriter w(file, kIntWritable, kDocument);
-  Document doc;
+  ByteWriter key, val;
   for (int64_t d = lo; d < hi; d++) {
-    int64_t b = c.row_ptr[d], e = c.row_ptr[d + 1];
+    const int64_t b = c.row_ptr[d], e = c.row_ptr[d + 1];
     if (e == b) continue;
-    doc.content.clear();
-    for (int64_t z = b; z < e; z++) doc.content.emplace_back(c.term_id[z], c.count[z]);
-    doc.gamma.assign(gamma + (size_t)(d - lo) * K, gamma + (size_t)(d - lo + 1) * K);
-    ByteWriter key, val;
+    key.buf.clear();
+    val.buf.clear();
     key.i32(c.doc_id[d]);
-    doc.write(val);
+    // Document.write (Document.java:241-263), straight from the CSR row and the gamma row
+    uint8_t *q = val.grow(8 + 8 * (size_t)(e - b) + 8 * (size_t)K);
+    ByteWriter::put32(q, (int32_t)(e - b));
+    q += 4;
+    for (int64_t z = b; z < e; z++) {
+      ByteWriter::put32(q, c.term_id[z]);
+      ByteWriter::put32(q + 4, c.count[z]);
+      q += 8;
+    }
+    ByteWriter::put32(q, K);
+    q += 4;
+    const double *g = gamma + (size_t)(d - lo) * K;
+    for (int k = 0; k < K; k++) {
+      int64_t bits;
+      memcpy(&bits, &g[k], 8);
+      ByteWriter::put64(q, bits);
+      q += 8;
+    }
     w.append(key, val);
   }
+  w.close();
+}
+
+// Part files one rank may write per gamma directory: rank r owns the indices [r * 32, r * 32 + 32),
+// so the name order of a directory is the document order whatever the rank count was.
+static const int kGammaPartsPerRank = 32;
+
+// The gamma output of one rank as several part files written concurrently, the way the map phase
+// writes one "gamma_gamma-m-NNNNN" per map task (VariationalInference.java:232-235,366-373): the
+// rank's documents are cut into contiguous pieces of about `bytes_per_part` bytes (at most
+// kGammaPartsPerRank, at most one per host thread), piece t going to index rank * 32 + t.  Returns
+// the number of part files.
+inline int write_gamma_parts(const std::string &dir, int rank, const Corpus &c, int64_t lo, int64_t hi,
+                             const double *gamma /* (hi-lo) x K */, int K,
+                             int64_t bytes_per_part = (int64_t)64 << 20) {
+  auto bytes_upto = [&](int64_t d) {  // serialized size of documents [lo, d), null-content ones included
+    return (c.row_ptr[d] - c.row_ptr[lo]) * 8 + (d - lo) * ((int64_t)K * 8 + 28);
+  };
+  const int64_t total = bytes_upto(hi);
+  const int parts = (int)std::max<int64_t>(
+      1, std::min<int64_t>({total / std::max<int64_t>(1, bytes_per_part) + 1, (int64_t)kGammaPartsPerRank,
+                            (int64_t)io_threads(kGammaPartsPerRank), std::max<int64_t>(1, hi - lo)}));
+  std::vector<int64_t> cut((size_t)parts + 1, hi);
+  cut[0] = lo;
+  for (int t = 1; t < parts; t++) {  // first document at which t/parts of the bytes are behind us
+    int64_t a = cut[(size_t)t - 1], b = hi;
+    const int64_t want = total * t / parts;
+    while (a < b) {
+      const int64_t m = (a + b) / 2;
+      if (bytes_upto(m) < want) a = m + 1; else b = m;
+    }
+    cut[(size_t)t] = a;
+  }
+  parallel_jobs((size_t)parts, [&](size_t t) {
+    char name[64];
+    snprintf(name, sizeof name, "/gamma_gamma-m-%05d", rank * kGammaPartsPerRank + (int)t);
+    write_gamma(dir + name, c, cut[t], cut[t + 1], gamma + (size_t)(cut[t] - lo) * K, K);
+  });
+  return parts;
 }
 
 // The eta file of -informedprior: SequenceFile<IntWritable topic (1-based), ArrayListOfIntsWritable
@@ -268,6 +485,7 @@ inline void write_eta(const std::string &path, const std::vector<std::vector<int
     for (int32_t x : seeds[t]) v.i32(x);
     w.append(k, v);
   }
+  w.close();
 }
 
 // java.lang.Double.toString: shortest digits that round-trip; decimal notation for

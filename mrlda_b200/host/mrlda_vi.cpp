@@ -351,9 +351,8 @@ int main(int argc, char **argv) {
         input_dir = o.output + "gamma-" + std::to_string(iteration + 1);
         mkdirs(input_dir);
         if (mrlda_get_gamma(ctx, gamma.data()) != MRLDA_OK) die(ctx, "mrlda_get_gamma");
-        char name[64];
-        snprintf(name, sizeof name, "/gamma_gamma-m-%05d", o.rank);
-        write_gamma(input_dir + name, all, lo, hi, gamma.data(), K);
+        // one part file per ~64 MB, written concurrently (the map phase's gamma_gamma-m-NNNNN files)
+        write_gamma_parts(input_dir, o.rank, all, lo, hi, gamma.data(), K);
         if (iteration != 0 && o.rank == 0 && is_own_gamma_dir(gamma_dir, o.output)) rm_rf(gamma_dir);
       }
       info("Log likelihood after iteration " + std::to_string(iteration + 1) + " is " + java_double(ll));

@@ -36,14 +36,22 @@ static const char *const kHMapIDW = "edu.umd.cloud9.io.map.HMapIDW";
 struct ByteWriter {
   std::vector<uint8_t> buf;
   void u8(uint8_t v) { buf.push_back(v); }
-  void i32(int32_t v) {
-    uint32_t u = (uint32_t)v;
-    for (int s = 24; s >= 0; s -= 8) buf.push_back((uint8_t)(u >> s));
+  // room for n more bytes; returns where they go (callers fill all n)
+  uint8_t *grow(size_t n) {
+    const size_t at = buf.size();
+    buf.resize(at + n);
+    return buf.data() + at;
   }
-  void i64(int64_t v) {
-    uint64_t u = (uint64_t)v;
-    for (int s = 56; s >= 0; s -= 8) buf.push_back((uint8_t)(u >> s));
+  static void put32(uint8_t *p, int32_t v) {
+    const uint32_t u = __builtin_bswap32((uint32_t)v);  // big-endian, as java.io.DataOutput writes
+    memcpy(p, &u, 4);
   }
+  static void put64(uint8_t *p, int64_t v) {
+    const uint64_t u = __builtin_bswap64((uint64_t)v);
+    memcpy(p, &u, 8);
+  }
+  void i32(int32_t v) { put32(grow(4), v); }
+  void i64(int64_t v) { put64(grow(8), v); }
   void f32(float v) {
     int32_t i;
     memcpy(&i, &v, 4);
@@ -90,17 +98,27 @@ struct ByteReader {
     need(1);
     return *p++;
   }
+  static int32_t get32(const uint8_t *q) {
+    uint32_t u;
+    memcpy(&u, q, 4);
+    return (int32_t)__builtin_bswap32(u);
+  }
+  static int64_t get64(const uint8_t *q) {
+    uint64_t u;
+    memcpy(&u, q, 8);
+    return (int64_t)__builtin_bswap64(u);
+  }
   int32_t i32() {
     need(4);
-    uint32_t u = 0;
-    for (int i = 0; i < 4; i++) u = (u << 8) | *p++;
-    return (int32_t)u;
+    const int32_t v = get32(p);
+    p += 4;
+    return v;
   }
   int64_t i64() {
     need(8);
-    uint64_t u = 0;
-    for (int i = 0; i < 8; i++) u = (u << 8) | *p++;
-    return (int64_t)u;
+    const int64_t v = get64(p);
+    p += 8;
+    return v;
   }
   float f32() {
     int32_t i = i32();
@@ -134,6 +152,48 @@ struct ByteReader {
   bool eof() const { return p >= end; }
 };
 
+// HMapII.put overwrites an existing key, so a repeated term id inside one Document record keeps its
+// first position and takes the last count.  Repeats are found with a small open-addressing table
+// (term id -> position) that is reused from record to record; `stamp` marks this record's slots.
+struct TermSlots {
+  void begin(size_t n) {
+    size_t slots = 16;
+    while (slots < n * 2) slots <<= 1;
+    if (key_.size() < slots) {
+      key_.assign(slots, 0);
+      pos_.assign(slots, 0);
+      stamp_of_.assign(slots, 0);
+      stamp_ = 0;
+    }
+    mask_ = key_.size() - 1;
+    if (++stamp_ == 0) {  // the 32-bit stamp wrapped: start over with clean slots
+      std::fill(stamp_of_.begin(), stamp_of_.end(), 0u);
+      stamp_ = 1;
+    }
+  }
+  // position of `id` among this record's entries, or -1 after remembering it at `pos`
+  int64_t find_or_add(int32_t id, int64_t pos) {
+    size_t h = ((uint32_t)id * 2654435761u) & mask_;
+    for (;;) {
+      if (stamp_of_[h] != stamp_) {
+        stamp_of_[h] = stamp_;
+        key_[h] = id;
+        pos_[h] = pos;
+        return -1;
+      }
+      if (key_[h] == id) return pos_[h];
+      h = (h + 1) & mask_;
+    }
+  }
+
+ private:
+  std::vector<int32_t> key_;
+  std::vector<int64_t> pos_;
+  std::vector<uint32_t> stamp_of_;
+  uint32_t stamp_ = 0;
+  size_t mask_ = 0;
+};
+
 // cc.mrlda.Document (Document.java:241-263 / :147-172)
 struct Document {
   std::vector<std::pair<int32_t, int32_t>> content;  // (termID, count); empty = null content
@@ -144,38 +204,56 @@ struct Document {
     return t;
   }
   void write(ByteWriter &w) const {
-    w.i32((int32_t)content.size());  // 0 when content == null
+    // one allocation, then straight stores: 4 + 8n + 4 + 8k bytes
+    uint8_t *q = w.grow(8 + 8 * content.size() + 8 * gamma.size());
+    ByteWriter::put32(q, (int32_t)content.size());  // 0 when content == null
+    q += 4;
     for (auto &e : content) {
-      w.i32(e.first);
-      w.i32(e.second);
+      ByteWriter::put32(q, e.first);
+      ByteWriter::put32(q + 4, e.second);
+      q += 8;
     }
-    w.i32((int32_t)gamma.size());  // 0 when gamma == null
-    for (double g : gamma) w.f64(g);
+    ByteWriter::put32(q, (int32_t)gamma.size());  // 0 when gamma == null
+    q += 4;
+    for (double g : gamma) {
+      int64_t bits;
+      memcpy(&bits, &g, 8);
+      ByteWriter::put64(q, bits);
+      q += 8;
+    }
   }
   void read(ByteReader &r) {
     content.clear();
     gamma.clear();
-    int32_t n = r.i32();
+    const int32_t n = r.i32();
     if (n > 0) {  // numEntries <= 0  =>  content = null
+      r.need((size_t)n * 8);
       content.reserve((size_t)n);
+      slots_.begin((size_t)n);
       for (int32_t i = 0; i < n; i++) {
-        int32_t id = r.i32(), c = r.i32();
-        bool dup = false;  // HMapII.put overwrites an existing key
-        for (auto &e : content)
-          if (e.first == id) {
-            e.second = c;
-            dup = true;
-            break;
-          }
-        if (!dup) content.emplace_back(id, c);
+        const int32_t id = ByteReader::get32(r.p), c = ByteReader::get32(r.p + 4);
+        r.p += 8;
+        const int64_t at = slots_.find_or_add(id, (int64_t)content.size());
+        if (at < 0)
+          content.emplace_back(id, c);
+        else
+          content[(size_t)at].second = c;
       }
     }
-    int32_t k = r.i32();
+    const int32_t k = r.i32();
     if (k > 0) {  // numTopics <= 0  =>  gamma = null
+      r.need((size_t)k * 8);
       gamma.resize((size_t)k);
-      for (int32_t i = 0; i < k; i++) gamma[i] = r.f64();
+      for (int32_t i = 0; i < k; i++) {
+        const int64_t bits = ByteReader::get64(r.p);
+        r.p += 8;
+        memcpy(&gamma[(size_t)i], &bits, 8);
+      }
     }
   }
+
+ private:
+  TermSlots slots_;
 };
 
 class SeqWriter {
@@ -183,6 +261,7 @@ class SeqWriter {
   SeqWriter(const std::string &path, const std::string &key_class, const std::string &value_class)
       : f_(fopen(path.c_str(), "wb")) {
     if (!f_) throw std::runtime_error("cannot create " + path);
+    setvbuf(f_, nullptr, _IOFBF, 1 << 20);  // records are a few KB: write them out 1 MB at a time
     ByteWriter h;
     h.bytes("SEQ", 3);
     h.u8(6);
@@ -202,7 +281,9 @@ class SeqWriter {
     h.bytes(sync_, 16);
     put(h.buf);
   }
-  ~SeqWriter() { close(); }
+  ~SeqWriter() {  // a destructor cannot report: writers call close() themselves to see flush errors
+    if (f_) fclose(f_);
+  }
   void append(const ByteWriter &key, const ByteWriter &value) {
     if (pos_ >= last_sync_ + 2000) {  // SequenceFile.Writer.checkAndWriteSync
       ByteWriter s;
@@ -211,23 +292,25 @@ class SeqWriter {
       put(s.buf);
       last_sync_ = pos_;
     }
-    ByteWriter r;
-    r.i32((int32_t)(key.buf.size() + value.buf.size()));
-    r.i32((int32_t)key.buf.size());
-    put(r.buf);
+    uint8_t head[8];
+    ByteWriter::put32(head, (int32_t)(key.buf.size() + value.buf.size()));
+    ByteWriter::put32(head + 4, (int32_t)key.buf.size());
+    put(head, 8);
     put(key.buf);
     put(value.buf);
   }
+  // flushes the buffered tail; a failed flush (disk full) is an error like a short write
   void close() {
-    if (f_) fclose(f_);
+    FILE *f = f_;
     f_ = nullptr;
+    if (f && fclose(f) != 0) throw std::runtime_error("short write (close)");
   }
 
  private:
-  void put(const std::vector<uint8_t> &b) {
-    if (!b.empty() && fwrite(b.data(), 1, b.size(), f_) != b.size())
-      throw std::runtime_error("short write");
-    pos_ += (int64_t)b.size();
+  void put(const std::vector<uint8_t> &b) { put(b.data(), b.size()); }
+  void put(const uint8_t *b, size_t n) {
+    if (n && fwrite(b, 1, n, f_) != n) throw std::runtime_error("short write");
+    pos_ += (int64_t)n;
   }
   FILE *f_;
   uint8_t sync_[16];
@@ -245,6 +328,7 @@ class SeqReader {
  public:
   explicit SeqReader(const std::string &path) : path_(path), f_(fopen(path.c_str(), "rb")) {
     if (!f_) throw std::runtime_error("cannot open " + path);
+    setvbuf(f_, nullptr, _IOFBF, 1 << 20);
     try {
       uint8_t magic[4];
       read_exact(magic, 4, "header");

@@ -51,7 +51,19 @@ int mrlda_io_write_corpus(const char *path, int64_t n_docs, const int64_t *row_p
           for (int64_t z = row_ptr[i]; z < row_ptr[i + 1]; z++) d.content.emplace_back(term[z], count[z]);
           if (gamma && k > 0) d.gamma.assign(gamma + (size_t)i * k, gamma + (size_t)(i + 1) * k);
           ByteWriter key, val; key.i32(doc_id ? doc_id[i] : (int32_t)i + 1); d.write(val); w.append(key, val);
-        } return 0;)
+        } w.close(); return 0;)
+}
+
+// the gamma output of one rank as concurrently written part files (write_gamma_parts); returns the
+// number of part files
+int mrlda_io_write_gamma_parts(const char *dir, int32_t rank, int64_t n_docs, const int64_t *row_ptr,
+                               const int32_t *term, const int32_t *count, const int32_t *doc_id,
+                               const double *gamma, int32_t k, int64_t bytes_per_part) {
+  GUARD(Corpus c; c.row_ptr.assign(row_ptr, row_ptr + n_docs + 1);
+        c.term_id.assign(term, term + row_ptr[n_docs]); c.count.assign(count, count + row_ptr[n_docs]);
+        c.doc_id.resize((size_t)n_docs);
+        for (int64_t i = 0; i < n_docs; i++) c.doc_id[(size_t)i] = doc_id ? doc_id[i] : (int32_t)i + 1;
+        return write_gamma_parts(dir, rank, c, 0, n_docs, gamma, k, bytes_per_part);)
 }
 
 struct mrlda_io_corpus { Corpus c; };
@@ -116,7 +128,7 @@ int mrlda_io_write_term_index(const char *path, int32_t n, const char *terms_nl)
         for (int32_t i = 1; i <= n; i++) {
           const char *e = strchr(p, '\n'); std::string t = e ? std::string(p, e) : std::string(p);
           ByteWriter k, v; k.i32(i); v.text(t); w.append(k, v); p = e ? e + 1 : p + t.size();
-        } return 0;)
+        } w.close(); return 0;)
 }
 // eta file of -informedprior: n (topic, term) pairs, topics 1..k
 int mrlda_io_write_eta(const char *path, int32_t k, int64_t n, const int32_t *topic, const int32_t *term) {

@@ -24,6 +24,8 @@ def load():
         L.mrlda_doc_deserialize.argtypes = [_bp, C.c_int64, _ip, _ip, C.c_int32, _ip, _dp, C.c_int32,
                                             _ip, _lp]
         L.mrlda_io_write_corpus.argtypes = [C.c_char_p, C.c_int64, _lp, _ip, _ip, _ip, _dp, C.c_int32]
+        L.mrlda_io_write_gamma_parts.argtypes = [C.c_char_p, C.c_int32, C.c_int64, _lp, _ip, _ip, _ip, _dp,
+                                                 C.c_int32, C.c_int64]
         L.mrlda_io_read_corpus.restype = C.c_void_p
         L.mrlda_io_read_corpus.argtypes = [C.c_char_p, C.c_int32, C.c_int32]
         L.mrlda_io_read_corpus_shard.restype = C.c_void_p
@@ -96,6 +98,27 @@ def write_corpus(path, row_ptr, term_id, count, doc_id=None, gamma=None, n_topic
                                      t.ctypes.data_as(_ip), c.ctypes.data_as(_ip),
                                      did.ctypes.data_as(_ip) if did is not None else None,
                                      g.ctypes.data_as(_dp) if g is not None else None, int(n_topics)))
+
+
+def write_gamma_parts(directory, rank, row_ptr, term_id, count, gamma, doc_id=None, bytes_per_part=64 << 20):
+    """One rank's gamma output as the driver writes it: gamma_gamma-m-NNNNN part files of about
+    bytes_per_part bytes each, written concurrently.  Returns the number of part files."""
+    rp = np.ascontiguousarray(row_ptr, dtype=np.int64)
+    t = np.ascontiguousarray(term_id, dtype=np.int32)
+    c = np.ascontiguousarray(count, dtype=np.int32)
+    g = np.ascontiguousarray(gamma, dtype=np.float64)
+    D = len(rp) - 1
+    if g.ndim != 2 or g.shape[0] != D or t.size < rp[D] or c.size < rp[D]:
+        raise ValueError("gamma must be D x K and term_id / count must cover row_ptr[D]")
+    did = np.ascontiguousarray(doc_id, dtype=np.int32) if doc_id is not None else None
+    if did is not None and did.size != D:
+        raise ValueError("doc_id must hold D values")
+    n = load().mrlda_io_write_gamma_parts(os.fsencode(directory), int(rank), D, rp.ctypes.data_as(_lp),
+                                          t.ctypes.data_as(_ip), c.ctypes.data_as(_ip),
+                                          did.ctypes.data_as(_ip) if did is not None else None,
+                                          g.ctypes.data_as(_dp), int(g.shape[1]), int(bytes_per_part))
+    _ck(n)
+    return n
 
 
 def read_corpus(path, n_topics, n_terms, rank=0, world=1):

@@ -248,3 +248,142 @@ def test_term_index_and_eta_files_cross_check(tmp_path):
         assert len(v) == 4 + 4 * n
         got[struct.unpack(">i", k)[0]] = list(struct.unpack_from(">%di" % n, v, 4))
     assert got == {1: [5, 9], 2: [], 3: [2]}  # one record per topic (InformedPrior.java:139-170)
+
+
+def _raw_document(entries, gamma=None):
+    """Document bytes from an entry LIST (so that a term id can repeat, which a dict cannot express)."""
+    out = struct.pack(">i", len(entries))
+    for t, c in entries:
+        out += struct.pack(">ii", t, c)
+    g = list(gamma) if gamma is not None else []
+    out += struct.pack(">i", len(g)) + b"".join(struct.pack(">d", x) for x in g)
+    return out
+
+
+def test_repeated_term_ids_close_the_gap_between_part_files(tmp_path, monkeypatch):
+    """HMapII.put overwrites: a term id repeated inside one record keeps its first position and takes
+    the last count.  The two-pass reader sizes the arrays from the scanned entry counts, so such
+    records leave their part file short and the following files have to move down — with one thread
+    and with several."""
+    rng = np.random.default_rng(5)
+    K = 3
+    files, want_docs = [], []
+    for f in range(4):
+        recs = []
+        for i in range(25):
+            n = int(rng.integers(0, 12))
+            ids = (rng.choice(60, n, replace=False) + 1).tolist()
+            entries = [(t, int(rng.integers(1, 9))) for t in ids]
+            if n >= 2 and (f in (0, 2)) and i % 3 == 0:  # repeat two ids with new counts
+                entries += [(ids[0], 77), (ids[1], 88), (ids[0], 99)]
+            merged = {}
+            for t, c in entries:
+                merged[t] = c  # dict keeps first position, last value: HMapII.put
+            g = rng.random(K).tolist()
+            doc_id = 100 * f + i
+            recs.append((struct.pack(">i", doc_id), _raw_document(entries, g)))
+            want_docs.append((doc_id, list(merged.items()), g))
+        files.append(recs)
+    d = tmp_path / "in"
+    d.mkdir()
+    for f, recs in enumerate(files):
+        pyseq.write_file(str(d / f"part-{f:05d}"), INT, DOC, recs, sync_every=5)
+    for threads in ("1", "4"):
+        monkeypatch.setenv("MRLDA_IO_THREADS", threads)
+        got = seqfile.read_corpus(str(d), K, 60)
+        assert got["doc_id"].tolist() == [x[0] for x in want_docs]
+        for i, (_, items, g) in enumerate(want_docs):
+            lo, hi = got["row_ptr"][i], got["row_ptr"][i + 1]
+            assert list(zip(got["term_id"][lo:hi].tolist(), got["count"][lo:hi].tolist())) == items
+            assert got["gamma"][i].tolist() == g
+        assert got["row_ptr"][-1] == len(got["term_id"]) == sum(len(x[1]) for x in want_docs)
+        # the splits of a sharded read see the same documents (bounds come from the scanned counts)
+        ids = []
+        for rank in range(3):
+            part = seqfile.read_corpus(str(d), K, 60, rank=rank, world=3)
+            lo = part["first_doc"]
+            for j in range(len(part["doc_id"])):
+                a, b = part["row_ptr"][j], part["row_ptr"][j + 1]
+                assert list(zip(part["term_id"][a:b].tolist(), part["count"][a:b].tolist())) == want_docs[lo + j][1]
+            assert part["gamma"] is not None and part["gamma"].shape == (len(part["doc_id"]), K)
+            ids += part["doc_id"].tolist()
+        assert ids == [x[0] for x in want_docs]
+
+
+def test_gamma_is_kept_only_when_every_kept_document_has_k_values(tmp_path):
+    """DocumentMapper.java:184: a stored gamma of another length is ignored; the CSR carries gamma only
+    when every document of the requested range has one of n_topics values."""
+    K = 4
+    a = [(struct.pack(">i", i), pyseq.document_bytes({1 + i: 2}, [0.5 + i] * K)) for i in range(6)]
+    b = [(struct.pack(">i", 10 + i), pyseq.document_bytes({3: 1, 4 + i: 1}, [1.0] * (K if i else K + 1))) for i in range(6)]
+    d = tmp_path / "in"
+    d.mkdir()
+    pyseq.write_file(str(d / "part-00000"), INT, DOC, a)
+    pyseq.write_file(str(d / "part-00001"), INT, DOC, b)
+    assert seqfile.read_corpus(str(d / "part-00000"), K, 20)["gamma"].shape == (6, K)
+    assert seqfile.read_corpus(str(d), K, 20)["gamma"] is None  # one record of part-00001 has K + 1 values
+    assert seqfile.read_corpus(str(d), K + 1, 20)["gamma"] is None
+    first = seqfile.read_corpus(str(d), K, 20, rank=0, world=3)  # a third of the entries: part-00000 alone
+    assert first["doc_id"].tolist() == list(range(6)) and first["gamma"].shape == (6, K)
+    with pytest.raises(seqfile.SeqFileError, match="term id"):
+        seqfile.read_corpus(str(d), K, 8)  # term ids above n_terms are refused in the second pass too
+
+
+@pytest.mark.parametrize("bytes_per_part", [1 << 30, 4096, 1])
+def test_gamma_part_files_round_trip(tmp_path, bytes_per_part):
+    """write_gamma_parts: the rank's documents as concurrently written gamma_gamma-m-NNNNN files,
+    rank r owning the indices from 32 r; read back in name order they are the documents (those with
+    null content dropped, DocumentMapper.java:197-201) with the gamma rows embedded."""
+    from mrlda_b200 import corpus
+    K = 5
+    c = corpus.generate(400, 300, K, 30, seed=9)
+    rp = c.row_ptr.copy()
+    # make documents 3 and 200 empty (null content): they must not be emitted
+    keep = np.ones(c.nnz, bool)
+    for dd in (3, 200):
+        keep[rp[dd]:rp[dd + 1]] = False
+    n = np.diff(rp)
+    n[[3, 200]] = 0
+    rp2 = np.concatenate([[0], np.cumsum(n)])
+    term, cnt = c.term_id[keep], c.count[keep]
+    gamma = np.random.default_rng(2).random((400, K))
+    ids = np.arange(400, dtype=np.int32) * 3 + 7
+    out = tmp_path / "gamma-1"
+    out.mkdir()
+    half = 180
+    sl = lambda a, b: (rp2[a:b + 1] - rp2[a], term[rp2[a]:rp2[b]], cnt[rp2[a]:rp2[b]])  # noqa: E731
+    n0 = seqfile.write_gamma_parts(str(out), 0, *sl(0, half), gamma[:half], doc_id=ids[:half], bytes_per_part=bytes_per_part)
+    n1 = seqfile.write_gamma_parts(str(out), 1, *sl(half, 400), gamma[half:], doc_id=ids[half:], bytes_per_part=bytes_per_part)
+    names = sorted(p.name for p in out.iterdir())
+    assert names == [f"gamma_gamma-m-{i:05d}" for i in range(n0)] + [f"gamma_gamma-m-{32 + i:05d}" for i in range(n1)]
+    assert (n0 == n1 == 1) if bytes_per_part == 1 << 30 else (2 <= n0 <= 32 and 2 <= n1 <= 32)
+    got = seqfile.read_corpus(str(out), K, 300)
+    kept = np.array([i for i in range(400) if i not in (3, 200)])
+    assert got["doc_id"].tolist() == ids[kept].tolist()
+    assert np.array_equal(got["gamma"], gamma[kept])
+    assert np.array_equal(got["term_id"], term) and np.array_equal(got["count"], cnt)
+    assert np.array_equal(np.diff(got["row_ptr"]), n[kept])
+    # and the independent Python reader agrees, file by file
+    seen = []
+    for name in names:
+        kc, vc, _, recs, _ = pyseq.read_file(str(out / name))
+        assert (kc, vc) == (INT, DOC)
+        for kb, vb in recs:
+            (doc_id,) = struct.unpack(">i", kb)
+            content, g = pyseq.parse_document(vb)[:2]
+            i = (doc_id - 7) // 3
+            assert content == dict(zip(term[rp2[i]:rp2[i + 1]].tolist(), cnt[rp2[i]:rp2[i + 1]].tolist()))
+            assert g == gamma[i].tolist()
+            seen.append(doc_id)
+    assert seen == ids[kept].tolist()
+
+
+def test_a_failed_flush_is_an_error_not_a_short_file():
+    """The writers buffer 1 MB; what the final flush cannot write (disk full) must surface."""
+    import os
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    with pytest.raises(seqfile.SeqFileError, match="short write"):
+        seqfile.write_corpus("/dev/full", [0, 1, 2], [1, 2], [3, 1])
+    with pytest.raises(seqfile.SeqFileError, match="short write"):
+        seqfile.write_alpha("/dev/full", [0.1, 0.2])
