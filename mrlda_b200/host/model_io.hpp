@@ -327,23 +327,51 @@ inline std::vector<double> read_alpha(const std::string &path, int n_topics) {
 
 // The TermReducer output (TermReducer.java:173-195,232-235): one record per topic,
 // key PairOfIntFloat(topic 1..K, (float) normaliser), value HMapIDW{term -> digamma(lambda)}.
+// dl is term-major (K contiguous), a record is one topic's column: eight topics (one cache line of
+// a row) are serialised together so that every line of dl is read once per eight records, and the
+// tiles of a wave are built concurrently; records are appended in topic order.
 inline void write_beta(const std::string &path, int K, int V, const double *dl, const float *nrm,
                        const uint8_t *present) {
   SeqWriter w(path, kPairOfIntFloat, kHMapIDW);
-  int32_t seen = 0;
-  for (int v = 0; v < V; v++) seen += present[v] ? 1 : 0;
-  for (int k = 0; k < K; k++) {
-    ByteWriter key, val;
-    key.i32(k + 1);
-    key.f32(nrm[k]);
-    val.buf.reserve((size_t)seen * 12 + 4);
-    val.i32(seen);
-    for (int v = 0; v < V; v++)
-      if (present[v]) {
-        val.i32(v + 1);
-        val.f64(dl[(size_t)v * K + k]);
+  std::vector<int32_t> terms;  // the terms that have a row (ascending)
+  for (int v = 0; v < V; v++)
+    if (present[v]) terms.push_back(v);
+  const size_t seen = terms.size(), rec_bytes = 4 + 12 * seen;
+  const int kTile = 8, tiles = (K + kTile - 1) / kTile;
+  const int wave = io_threads((size_t)tiles);
+  std::vector<ByteWriter> val((size_t)wave * kTile);
+  for (int t0 = 0; t0 < tiles; t0 += wave) {
+    const int nt = std::min(wave, tiles - t0);
+    parallel_jobs((size_t)nt, [&](size_t j) {
+      const int k0 = (t0 + (int)j) * kTile, kn = std::min(kTile, K - k0);
+      uint8_t *q[kTile];
+      for (int i = 0; i < kn; i++) {
+        ByteWriter &b = val[j * kTile + (size_t)i];
+        b.buf.clear();
+        q[i] = b.grow(rec_bytes);
+        ByteWriter::put32(q[i], (int32_t)seen);
+        q[i] += 4;
       }
-    w.append(key, val);
+      for (size_t s = 0; s < seen; s++) {
+        const int32_t v = terms[s];
+        const double *row = dl + (size_t)v * K + k0;
+        for (int i = 0; i < kn; i++) {
+          int64_t bits;
+          memcpy(&bits, &row[i], 8);
+          ByteWriter::put32(q[i], v + 1);
+          ByteWriter::put64(q[i] + 4, bits);
+          q[i] += 12;
+        }
+      }
+    });
+    for (int j = 0; j < nt; j++)
+      for (int i = 0; i < kTile && (t0 + j) * kTile + i < K; i++) {
+        const int k = (t0 + j) * kTile + i;
+        ByteWriter key;
+        key.i32(k + 1);
+        key.f32(nrm[k]);
+        w.append(key, val[(size_t)j * kTile + (size_t)i]);
+      }
   }
   w.close();
 }

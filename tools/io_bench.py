@@ -51,5 +51,13 @@ try:
         assert np.array_equal(r["row_ptr"], c.row_ptr) and np.array_equal(r["term_id"], c.term_id)
         assert np.array_equal(r["count"], c.count) and (not with_gamma or np.array_equal(r["gamma"], g))
         timed(f"read  shard 1 of 2, {tag}", lambda: seqfile.read_corpus(d, K, V, rank=1, world=2), size_of(d) / 2)
+    # the driver's own gamma output path: concurrent part files of about 64 MB
+    d = os.path.join(root, "gamma-parts")
+    os.makedirs(d)
+    n = timed("write_gamma_parts (driver path)",
+              lambda: seqfile.write_gamma_parts(d, 0, c.row_ptr, c.term_id, c.count, g), lambda: size_of(d))
+    print(f"  -> {n} part file(s), {os.cpu_count()} host threads visible")
+    r = seqfile.read_corpus(d, K, V)
+    assert np.array_equal(r["gamma"], g) and np.array_equal(r["term_id"], c.term_id)
 finally:
     shutil.rmtree(root)
