@@ -17,6 +17,7 @@ PIF = "edu.umd.cloud9.io.pair.PairOfIntFloat"
 HMAP = "edu.umd.cloud9.io.map.HMapIDW"
 
 
+@settings(deadline=None)
 @given(st.integers(min_value=-(2 ** 63), max_value=2 ** 63 - 1))
 def test_vint_round_trip(i):
     b = pyseq.write_vint(i)
