@@ -25,7 +25,12 @@ public final class CsrCorpus {
   public int[] termId = new int[0];
   public int[] count = new int[0];
   public int[] docId = new int[0];
-  /** D*K stored gamma values, or null when no document of the input carries a gamma. */
+  /**
+   * D*K stored gamma values, or null unless EVERY document of the input carries a gamma of
+   * numberOfTopics values (the rule of the native reader, mrlda_b200/host/model_io.hpp: a gamma
+   * of another length is ignored, DocumentMapper.java:184, and a partly filled array would hand
+   * the kernels zero rows).
+   */
   public double[] gammaOrNull = null;
   public int numberOfDocuments = 0;
 
@@ -38,6 +43,7 @@ public final class CsrCorpus {
     int[] termId = new int[1 << 14];
     int[] count = new int[1 << 14];
     double[] gamma = null;
+    boolean allGamma = true;
     int d = 0;
     long z = 0;
     FileStatus[] parts = fs.isFile(dir) ? new FileStatus[] {fs.getFileStatus(dir)} : fs.listStatus(dir);
@@ -76,11 +82,15 @@ public final class CsrCorpus {
             }
           }
           double[] g = value.getGamma();
-          if (g != null && g.length == numberOfTopics) {
+          if (allGamma && g != null && g.length == numberOfTopics
+              && (long) docId.length * numberOfTopics <= Integer.MAX_VALUE) {
             if (gamma == null) {
               gamma = new double[docId.length * numberOfTopics];
             }
             System.arraycopy(g, 0, gamma, d * numberOfTopics, numberOfTopics);
+          } else {
+            allGamma = false; // one document without a K-vector: the whole input starts cold
+            gamma = null;
           }
           d++;
           rowPtr[d] = z;
@@ -94,7 +104,7 @@ public final class CsrCorpus {
     c.docId = Arrays.copyOf(docId, d);
     c.termId = Arrays.copyOf(termId, (int) z);
     c.count = Arrays.copyOf(count, (int) z);
-    c.gammaOrNull = gamma == null ? null : Arrays.copyOf(gamma, d * numberOfTopics);
+    c.gammaOrNull = (!allGamma || gamma == null) ? null : Arrays.copyOf(gamma, d * numberOfTopics);
     return c;
   }
 }
