@@ -328,50 +328,80 @@ inline std::vector<double> read_alpha(const std::string &path, int n_topics) {
 // The TermReducer output (TermReducer.java:173-195,232-235): one record per topic,
 // key PairOfIntFloat(topic 1..K, (float) normaliser), value HMapIDW{term -> digamma(lambda)}.
 // dl is term-major (K contiguous), a record is one topic's column: eight topics (one cache line of
-// a row) are serialised together so that every line of dl is read once per eight records, and the
-// tiles of a wave are built concurrently; records are appended in topic order.
+// a row) are serialised together so that every line of dl is read once per eight records.  All
+// records have one size, so their file positions (sync escapes included) are known in advance
+// (SeqWriter::plan): the tiles are built concurrently and each stores its own bytes with pwrite —
+// the file is byte for byte what appending the records one after another gives (and that is what
+// happens with a single thread).
 inline void write_beta(const std::string &path, int K, int V, const double *dl, const float *nrm,
                        const uint8_t *present) {
   SeqWriter w(path, kPairOfIntFloat, kHMapIDW);
   std::vector<int32_t> terms;  // the terms that have a row (ascending)
   for (int v = 0; v < V; v++)
     if (present[v]) terms.push_back(v);
-  const size_t seen = terms.size(), rec_bytes = 4 + 12 * seen;
+  const size_t seen = terms.size(), val_bytes = 4 + 12 * seen, key_bytes = 8, rec_bytes = 8 + key_bytes + val_bytes;
   const int kTile = 8, tiles = (K + kTile - 1) / kTile;
-  const int wave = io_threads((size_t)tiles);
-  std::vector<ByteWriter> val((size_t)wave * kTile);
-  for (int t0 = 0; t0 < tiles; t0 += wave) {
-    const int nt = std::min(wave, tiles - t0);
-    parallel_jobs((size_t)nt, [&](size_t j) {
-      const int k0 = (t0 + (int)j) * kTile, kn = std::min(kTile, K - k0);
-      uint8_t *q[kTile];
+  // fills dst[i] (val_bytes each) with the HMapIDW values of topics k0 .. k0 + kn - 1
+  auto build = [&](int k0, int kn, uint8_t *const *dst) {
+    uint8_t *q[kTile];
+    for (int i = 0; i < kn; i++) {
+      q[i] = dst[i];
+      ByteWriter::put32(q[i], (int32_t)seen);
+      q[i] += 4;
+    }
+    for (size_t s = 0; s < seen; s++) {
+      const int32_t v = terms[s];
+      const double *row = dl + (size_t)v * K + k0;
       for (int i = 0; i < kn; i++) {
-        ByteWriter &b = val[j * kTile + (size_t)i];
-        b.buf.clear();
-        q[i] = b.grow(rec_bytes);
-        ByteWriter::put32(q[i], (int32_t)seen);
-        q[i] += 4;
+        int64_t bits;
+        memcpy(&bits, &row[i], 8);
+        ByteWriter::put32(q[i], v + 1);
+        ByteWriter::put64(q[i] + 4, bits);
+        q[i] += 12;
       }
-      for (size_t s = 0; s < seen; s++) {
-        const int32_t v = terms[s];
-        const double *row = dl + (size_t)v * K + k0;
-        for (int i = 0; i < kn; i++) {
-          int64_t bits;
-          memcpy(&bits, &row[i], 8);
-          ByteWriter::put32(q[i], v + 1);
-          ByteWriter::put64(q[i] + 4, bits);
-          q[i] += 12;
-        }
+    }
+  };
+  if (io_threads((size_t)tiles) <= 1) {
+    std::vector<ByteWriter> val((size_t)kTile);
+    for (int t = 0; t < tiles; t++) {
+      const int k0 = t * kTile, kn = std::min(kTile, K - k0);
+      uint8_t *dst[kTile];
+      for (int i = 0; i < kn; i++) {
+        val[(size_t)i].buf.clear();
+        dst[i] = val[(size_t)i].grow(val_bytes);
       }
-    });
-    for (int j = 0; j < nt; j++)
-      for (int i = 0; i < kTile && (t0 + j) * kTile + i < K; i++) {
-        const int k = (t0 + j) * kTile + i;
+      build(k0, kn, dst);
+      for (int i = 0; i < kn; i++) {
         ByteWriter key;
-        key.i32(k + 1);
-        key.f32(nrm[k]);
-        w.append(key, val[(size_t)j * kTile + (size_t)i]);
+        key.i32(k0 + i + 1);
+        key.f32(nrm[k0 + i]);
+        w.append(key, val[(size_t)i]);
       }
+    }
+  } else {
+    const std::vector<SeqWriter::Slot> slot = w.plan((size_t)K, rec_bytes);
+    parallel_jobs((size_t)tiles, [&](size_t t) {
+      const int k0 = (int)t * kTile, kn = std::min(kTile, K - k0);
+      // one buffer from the tile's first byte (its sync escape, if any) to the end of its last record
+      const int64_t from = slot[(size_t)k0].at - (slot[(size_t)k0].sync_before ? 20 : 0);
+      const int64_t to = slot[(size_t)(k0 + kn - 1)].at + (int64_t)rec_bytes;
+      std::vector<uint8_t> buf((size_t)(to - from));
+      uint8_t *dst[kTile];
+      for (int i = 0; i < kn; i++) {
+        const SeqWriter::Slot &sl = slot[(size_t)(k0 + i)];
+        uint8_t *rec = buf.data() + (sl.at - from);
+        if (sl.sync_before) w.sync_escape(rec - 20);
+        ByteWriter::put32(rec, (int32_t)(key_bytes + val_bytes));
+        ByteWriter::put32(rec + 4, (int32_t)key_bytes);
+        ByteWriter::put32(rec + 8, k0 + i + 1);
+        int32_t fbits;
+        memcpy(&fbits, &nrm[k0 + i], 4);
+        ByteWriter::put32(rec + 12, fbits);
+        dst[i] = rec + 16;
+      }
+      build(k0, kn, dst);
+      w.write_at(from, buf.data(), buf.size());
+    });
   }
   w.close();
 }

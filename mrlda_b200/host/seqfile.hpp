@@ -23,6 +23,7 @@
 #include <utility>
 #include <vector>
 
+#include <unistd.h>
 #include <zlib.h>
 
 namespace mrlda_host {
@@ -298,6 +299,44 @@ class SeqWriter {
     put(head, 8);
     put(key.buf);
     put(value.buf);
+  }
+  // Positions of n further records of rec_bytes each (8-byte record header + key + value), exactly
+  // where append() would put them, for writers that build records concurrently and store them with
+  // write_at(): `at` is where the record header goes; with sync_before the 20 bytes in front of it
+  // are a sync escape (sync_escape()).  The writer's position moves behind the last record; the
+  // caller must fill every planned byte before close().
+  struct Slot {
+    int64_t at;
+    bool sync_before;
+  };
+  std::vector<Slot> plan(size_t n, size_t rec_bytes) {
+    if (fflush(f_) != 0) throw std::runtime_error("short write");
+    std::vector<Slot> slots(n);
+    for (size_t i = 0; i < n; i++) {
+      const bool sync = pos_ >= last_sync_ + 2000;
+      if (sync) {
+        pos_ += 20;
+        last_sync_ = pos_;
+      }
+      slots[i] = Slot{pos_, sync};
+      pos_ += (int64_t)rec_bytes;
+    }
+    if (fseeko(f_, (off_t)pos_, SEEK_SET) != 0) throw std::runtime_error("cannot seek");
+    return slots;
+  }
+  void sync_escape(uint8_t *dst) const {  // 20 bytes
+    ByteWriter::put32(dst, -1);
+    memcpy(dst + 4, sync_, 16);
+  }
+  void write_at(int64_t at, const uint8_t *b, size_t n) const {  // thread-safe (pwrite)
+    const int fd = fileno(f_);
+    while (n > 0) {
+      const ssize_t w = pwrite(fd, b, n, (off_t)at);
+      if (w <= 0) throw std::runtime_error("short write");
+      b += w;
+      at += w;
+      n -= (size_t)w;
+    }
   }
   // flushes the buffered tail; a failed flush (disk full) is an error like a short write
   void close() {

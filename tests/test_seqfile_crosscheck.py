@@ -388,3 +388,33 @@ def test_a_failed_flush_is_an_error_not_a_short_file():
         seqfile.write_corpus("/dev/full", [0, 1, 2], [1, 2], [3, 1])
     with pytest.raises(seqfile.SeqFileError, match="short write"):
         seqfile.write_alpha("/dev/full", [0.1, 0.2])
+
+
+@pytest.mark.parametrize("K,V,frac", [(3, 10, 0.5), (8, 1, 1.0), (17, 40, 1.0), (64, 170, 0.9), (203, 900, 0.7)])
+def test_concurrent_beta_writer_is_byte_identical_to_appending(tmp_path, monkeypatch, K, V, frac):
+    """write_beta plans every record's position (sync escapes included) and lets the tiles store their
+    own bytes; the file must be exactly what appending the records one by one produces, for records
+    smaller and larger than the 2000-byte sync interval, and must read back through both readers."""
+    rng = np.random.default_rng(K)
+    dl = rng.standard_normal((V, K))
+    nm = rng.random(K).astype(np.float32)
+    pr = (rng.random(V) < frac).astype(np.uint8)
+    pr[0] = 1
+    files = {}
+    for threads in ("1", "5"):
+        monkeypatch.setenv("MRLDA_IO_THREADS", threads)
+        # the same path both times: the sync marker is derived from it
+        path = tmp_path / "beta-1"
+        seqfile.write_beta(str(path), dl, nm, pr)
+        files[threads] = path.read_bytes()
+    assert files["1"] == files["5"]
+    got = seqfile.read_beta(str(tmp_path / "beta-1"), K, V)
+    m = pr.astype(bool)
+    assert np.array_equal(got[0][m], dl[m]) and np.array_equal(got[1], nm) and np.array_equal(got[2], pr)
+    kc, vc, _, recs, escapes = pyseq.read_file(str(tmp_path / "beta-1"))
+    assert (kc, vc) == (PIF, HMAP) and len(recs) == K
+    for k, (kb, vb) in enumerate(recs):
+        topic, norm = struct.unpack(">if", kb)
+        assert topic == k + 1 and np.float32(norm) == nm[k]
+        (n,) = struct.unpack_from(">i", vb, 0)
+        assert n == int(m.sum()) and len(vb) == 4 + 12 * n
