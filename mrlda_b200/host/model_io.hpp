@@ -406,40 +406,104 @@ inline void write_beta(const std::string &path, int K, int V, const double *dl, 
   w.close();
 }
 
-// importBeta's parse (DocumentMapper.java:475-536) into the arrays mrlda_set_beta takes.
+// importBeta's parse (DocumentMapper.java:475-536) into the arrays mrlda_set_beta takes.  A record
+// is one topic's column of the term-major matrix, so storing it entry by entry touches one cache
+// line per value: records are taken eight at a time and walked in lockstep (HMapIDW files written
+// from one key set list the terms in one order), which puts up to eight values into each line, and
+// the tiles of a wave are scattered concurrently (distinct topics: distinct cells).  A topic that
+// appears twice is handled on its own so that "Dual initialization" is reported as the reference
+// reports it.
 inline void read_beta(const std::string &path, int K, int V, std::vector<double> &dl,
                       std::vector<float> &nrm, std::vector<uint8_t> &present) {
   SeqReader r(path);
   if (r.key_class != kPairOfIntFloat || r.value_class != kHMapIDW)
     throw std::invalid_argument(path + ": not a beta file");
-  dl.assign((size_t)V * K, 0.0);
+  dl.clear();
+  alloc_huge(dl, (size_t)V * K);
   nrm.assign((size_t)K, 0.0f);
   present.assign((size_t)V, 0);
-  std::vector<uint8_t> cell((size_t)V * K, 0);
+  std::vector<uint8_t> cell;
+  alloc_huge(cell, (size_t)V * K);
+  struct Rec {
+    int32_t topic = 0, n = 0;
+    const uint8_t *data = nullptr;  // n x (int32 term, float64 value)
+    std::vector<uint8_t> own;       // the copy `data` points to when the record waits for its wave
+  };
+  const int kTile = 8;
+  const bool direct = io_threads(64) <= 1;  // one thread: store every record as it is read, no copy
+  const size_t wave = direct ? 1 : (size_t)io_threads(64) * kTile;
+  std::vector<Rec> recs(wave);
+  std::vector<uint8_t> topic_seen((size_t)K, 0);
+  size_t have = 0;
+  auto store = [&](const Rec *tile, int cnt) {  // the records of one tile, in lockstep where they agree
+    int32_t n_min = tile[0].n;
+    for (int i = 1; i < cnt; i++) n_min = std::min(n_min, tile[i].n);
+    for (int32_t s = 0; s < n_min; s++) {
+      for (int i = 0; i < cnt; i++) {
+        const uint8_t *e = tile[i].data + (size_t)s * 12;
+        const int32_t term = ByteReader::get32(e);
+        if (term < 1 || term > V)
+          throw std::invalid_argument("beta file: term id " + std::to_string(term) + " out of range");
+        const size_t at = (size_t)(term - 1) * K + (size_t)(tile[i].topic - 1);
+        if (cell[at])
+          throw std::invalid_argument("Dual initialization for term " + std::to_string(term) +
+                                      " in topic " + std::to_string(tile[i].topic - 1) + "...");
+        cell[at] = 1;
+        const int64_t bits = ByteReader::get64(e + 4);
+        memcpy(&dl[at], &bits, 8);
+      }
+    }
+    for (int i = 0; i < cnt; i++)  // what the longer records hold beyond the shortest
+      for (int32_t s = n_min; s < tile[i].n; s++) {
+        const uint8_t *e = tile[i].data + (size_t)s * 12;
+        const int32_t term = ByteReader::get32(e);
+        if (term < 1 || term > V)
+          throw std::invalid_argument("beta file: term id " + std::to_string(term) + " out of range");
+        const size_t at = (size_t)(term - 1) * K + (size_t)(tile[i].topic - 1);
+        if (cell[at])
+          throw std::invalid_argument("Dual initialization for term " + std::to_string(term) +
+                                      " in topic " + std::to_string(tile[i].topic - 1) + "...");
+        cell[at] = 1;
+        const int64_t bits = ByteReader::get64(e + 4);
+        memcpy(&dl[at], &bits, 8);
+      }
+  };
+  auto flush = [&] {
+    const size_t tiles = (have + kTile - 1) / kTile;
+    parallel_jobs(tiles, [&](size_t t) {
+      store(&recs[t * kTile], (int)std::min<size_t>(kTile, have - t * kTile));
+    });
+    have = 0;
+  };
   const uint8_t *k, *v;
   size_t kl, vl;
   while (r.next(k, kl, v, vl)) {
     ByteReader kr(k, kl), vr(v, vl);
-    int32_t topic = kr.i32();
-    float norm = kr.f32();
+    const int32_t topic = kr.i32();
+    const float norm = kr.f32();
     if (!(topic > 0 && topic <= K))
       throw std::invalid_argument("Invalid beta vector for term " + std::to_string(topic) + "...");
     nrm[(size_t)topic - 1] = norm;
-    int32_t n = vr.i32();
-    for (int32_t i = 0; i < n; i++) {
-      int32_t term = vr.i32();
-      double val = vr.f64();
-      if (term < 1 || term > V)
-        throw std::invalid_argument("beta file: term id " + std::to_string(term) + " out of range");
-      size_t at = (size_t)(term - 1) * K + (size_t)(topic - 1);
-      if (cell[at])
-        throw std::invalid_argument("Dual initialization for term " + std::to_string(term) +
-                                    " in topic " + std::to_string(topic - 1) + "...");
-      cell[at] = 1;
-      dl[at] = val;
-      present[(size_t)term - 1] = 1;
+    const int32_t n = vr.i32();
+    if (n < 0) continue;  // an empty map
+    vr.need((size_t)n * 12);
+    const bool repeat = topic_seen[(size_t)topic - 1] != 0;
+    topic_seen[(size_t)topic - 1] = 1;
+    if (repeat) flush();  // its cells may collide with a record of the wave: keep the order
+    Rec &rec = recs[have++];
+    rec.topic = topic;
+    rec.n = n;
+    if (direct) {
+      rec.data = vr.p;  // valid until the next r.next(): stored right away
+    } else {
+      rec.own.assign(vr.p, vr.p + (size_t)n * 12);
+      rec.data = rec.own.data();
     }
+    if (repeat || have == wave) flush();
   }
+  flush();
+  for (int v = 0; v < V; v++)  // a term is present when any topic's record listed it
+    present[(size_t)v] = memchr(&cell[(size_t)v * K], 1, (size_t)K) ? 1 : 0;
 }
 
 // The "gamma" named output: the input documents with the updated gamma embedded

@@ -418,3 +418,51 @@ def test_concurrent_beta_writer_is_byte_identical_to_appending(tmp_path, monkeyp
         assert topic == k + 1 and np.float32(norm) == nm[k]
         (n,) = struct.unpack_from(">i", vb, 0)
         assert n == int(m.sum()) and len(vb) == 4 + 12 * n
+
+
+def _hmap(entries):
+    return struct.pack(">i", len(entries)) + b"".join(struct.pack(">id", t, x) for t, x in entries)
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+def test_beta_reader_takes_any_record_and_term_order(tmp_path, monkeypatch, threads):
+    """importBeta accepts the topics in any order, each with its own term order and its own subset of
+    terms (HMapIDW iteration order is arbitrary); the tiled reader must too, with one thread and with
+    several, and report a cell that is initialised twice (DocumentMapper.java:514-518)."""
+    monkeypatch.setenv("MRLDA_IO_THREADS", threads)
+    K, V = 21, 57
+    rng = np.random.default_rng(8)
+    want = np.zeros((V, K))
+    nm = rng.random(K).astype(np.float32)
+    recs = []
+    for k in rng.permutation(K):
+        terms = rng.permutation(V)[: int(rng.integers(1, V + 1))] + 1
+        vals = rng.standard_normal(len(terms))
+        want[terms - 1, k] = vals
+        recs.append((struct.pack(">if", int(k) + 1, float(nm[k])), _hmap(list(zip(terms.tolist(), vals.tolist())))))
+    recs.insert(5, (struct.pack(">if", 3, 0.0), _hmap([])))  # an empty map for a topic is legal
+    nm_want = nm.copy()
+    path = tmp_path / "beta-7"
+    pyseq.write_file(str(path), PIF, HMAP, recs, sync_every=4)
+    dl, got_nm, present = seqfile.read_beta(str(path), K, V)
+    assert np.array_equal(dl, want)
+    topics_in_order = [struct.unpack(">if", kb) for kb, _ in recs]
+    for t, x in topics_in_order:
+        nm_want[t - 1] = np.float32(x)  # last record of a topic wins
+    assert np.array_equal(got_nm, nm_want)
+    assert np.array_equal(present, (want != 0).any(1).astype(np.uint8))
+    # the same cell in two records of one topic
+    bad = recs + [(struct.pack(">if", 2, 1.0), _hmap([(int(np.flatnonzero(want[:, 1])[0]) + 1, 9.0)]))]
+    pyseq.write_file(str(tmp_path / "beta-8"), PIF, HMAP, bad)
+    with pytest.raises(seqfile.SeqFileError, match="Dual initialization"):
+        seqfile.read_beta(str(tmp_path / "beta-8"), K, V)
+    # ... and inside one record
+    pyseq.write_file(str(tmp_path / "beta-9"), PIF, HMAP, [(struct.pack(">if", 1, 1.0), _hmap([(4, 1.0), (5, 2.0), (4, 3.0)]))])
+    with pytest.raises(seqfile.SeqFileError, match="Dual initialization"):
+        seqfile.read_beta(str(tmp_path / "beta-9"), K, V)
+    pyseq.write_file(str(tmp_path / "beta-10"), PIF, HMAP, [(struct.pack(">if", 1, 1.0), _hmap([(V + 1, 1.0)]))])
+    with pytest.raises(seqfile.SeqFileError, match="out of range"):
+        seqfile.read_beta(str(tmp_path / "beta-10"), K, V)
+    pyseq.write_file(str(tmp_path / "beta-11"), PIF, HMAP, [(struct.pack(">if", K + 1, 1.0), _hmap([(1, 1.0)]))])
+    with pytest.raises(seqfile.SeqFileError, match="Invalid beta vector"):
+        seqfile.read_beta(str(tmp_path / "beta-11"), K, V)
