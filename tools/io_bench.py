@@ -59,5 +59,12 @@ try:
     print(f"  -> {n} part file(s), {os.cpu_count()} host threads visible")
     r = seqfile.read_corpus(d, K, V)
     assert np.array_equal(r["gamma"], g) and np.array_equal(r["term_id"], c.term_id)
+    # the model file of one iteration: beta-N (K records of V values each)
+    dl = np.random.default_rng(2).standard_normal((V, K))
+    nm, pr = np.ones(K, np.float32), np.ones(V, np.uint8)
+    bp = os.path.join(root, "beta-1")
+    timed("write_beta", lambda: seqfile.write_beta(bp, dl, nm, pr), lambda: os.path.getsize(bp))
+    rb = timed("read_beta", lambda: seqfile.read_beta(bp, K, V), os.path.getsize(bp))
+    assert np.array_equal(rb[0], dl)
 finally:
     shutil.rmtree(root)
