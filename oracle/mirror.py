@@ -11,6 +11,7 @@ was not written by looking at that file: the functions below were written from t
   * TermCombiner.reduce         TermCombiner.java:19-35
   * TermReducer.reduce / close  TermReducer.java:134-238
   * DocumentMapper.importBeta   DocumentMapper.java:475-536
+  * updateVectorAlpha / updateScalarAlpha   VariationalInference.java:409-511, :573-625
 
 and agree with the C oracle to <= 1e-13 relative (tests/test_oracle_mirror.py).  The reference
 itself cannot run in this image (Java/Hadoop, no JVM), so this is an independent-restatement pin,
@@ -201,3 +202,114 @@ def map_document_mp(term_id, count, logbeta, alpha, sweeps=99, dps=40):
     ll = (mp.loggamma(sum(al)) - sum(mp.loggamma(a) for a in al)) + (sum(mp.loggamma(g) for g in gam)
                                                                       - mp.loggamma(sg)) + lik_phi
     return ([float(g) for g in gam], [[float(v) for v in r] for r in log_phi], float(ll))
+
+
+# ---------------------------------------------------------------------------------------------
+# Driver-side alpha update, written from VariationalInference.java:409-511 (updateVectorAlpha) and
+# :573-625 (updateScalarAlpha) alone.  Java arrays are references: `alphaVectorUpdate =
+# alphaVector` (:471) and `alphaVector = alphaVectorUpdate` (:500) make the two names one array, so
+# Python lists (also references) restate the aliasing literally.  Constants are the float literals
+# of Settings.java:60-63,68 widened to double, as Java widens them.
+ALPHA_CONVERGE = float(np.float32(0.000001))  # DEFAULT_ALPHA_UPDATE_CONVERGE_THRESHOLD
+ALPHA_MAX_ITER = 1000
+ALPHA_MAX_DECAY = 10
+ALPHA_DECAY = float(np.float32(0.8))  # DEFAULT_ALPHA_UPDATE_DECAY_FACTOR
+ALPHA_SCALE = 10
+
+
+def trigamma(x):
+    """cloud9 Gamma.trigamma (lda-c series), scalar, literal operation order."""
+    x = float(x) + 6.0
+    p = 1.0 / (x * x)
+    p = (((((0.075757575757576 * p - 0.033333333333333) * p + 0.0238095238095238) * p - 0.033333333333333) * p
+          + 0.166666666666667) * p + 1.0) / x + 0.5 * p
+    for _ in range(6):
+        x = x - 1.0
+        p = 1.0 / (x * x) + p
+    return p
+
+
+def _digamma1(x):
+    return float(digamma(np.float64(x)))
+
+
+def update_vector_alpha(n_topics, n_docs, alpha, ss):
+    """VariationalInference.updateVectorAlpha as written, aliasing included."""
+    f = np.float64
+    alpha_vector = [f(a) for a in alpha]
+    ss = [f(s) for s in ss]
+    update = [f(0.0)] * n_topics
+    grad = [f(0.0)] * n_topics
+    hess = [f(0.0)] * n_topics
+    count = 0
+    keep_going = True
+    decay = 0
+    with np.errstate(all="ignore"):
+        alpha_sum = f(0.0)
+        for j in range(n_topics):
+            alpha_sum = alpha_sum + alpha_vector[j]
+        while keep_going:
+            sum_g_h = f(0.0)
+            sum_1_h = f(0.0)
+            for i in range(n_topics):
+                grad[i] = f(n_docs) * (f(_digamma1(alpha_sum)) - f(_digamma1(alpha_vector[i]))) + ss[i]
+                hess[i] = f(-n_docs) * f(trigamma(alpha_vector[i]))
+                if np.isinf(grad[i]):
+                    return np.array(alpha_vector, dtype=np.float64)  # ArithmeticException, caught at :505
+                sum_g_h = sum_g_h + grad[i] / hess[i]
+                sum_1_h = sum_1_h + f(1.0) / hess[i]
+            z = f(n_docs) * f(trigamma(alpha_sum))
+            c = sum_g_h / (f(1.0) / z + sum_1_h)
+            while True:
+                singular = False
+                for i in range(n_topics):
+                    step = f(math.pow(ALPHA_DECAY, decay)) * (grad[i] - c) / hess[i]
+                    if alpha_vector[i] <= step:
+                        singular = True
+                        break
+                    update[i] = alpha_vector[i] - step
+                if singular:
+                    decay += 1
+                    update = alpha_vector  # :471, the two names are one array from here on
+                    if decay > ALPHA_MAX_DECAY:
+                        break
+                else:
+                    break
+            alpha_sum = f(0.0)
+            keep_going = False
+            for j in range(n_topics):
+                alpha_sum = alpha_sum + update[j]
+                if abs((update[j] - alpha_vector[j]) / alpha_vector[j]) >= ALPHA_CONVERGE:
+                    keep_going = True
+            if count >= ALPHA_MAX_ITER:
+                keep_going = False
+            if decay > ALPHA_MAX_DECAY:
+                break
+            count += 1
+            alpha_vector = update  # :500
+    return np.array(alpha_vector, dtype=np.float64)
+
+
+def update_scalar_alpha(n_topics, n_docs, alpha_init, ss):
+    """VariationalInference.updateScalarAlpha as written (log-space Newton on a symmetric alpha)."""
+    f = np.float64
+    alpha_init = f(alpha_init)
+    ss = f(ss)
+    count = 0
+    update = alpha_init
+    K = f(n_topics)
+    with np.errstate(all="ignore"):
+        while True:
+            count += 1
+            if np.isnan(update) or np.isinf(update):
+                alpha_init = alpha_init * f(ALPHA_SCALE)
+                update = alpha_init
+            alpha_sum = update * K
+            g = f(n_docs) * (K * f(_digamma1(alpha_sum)) - K * f(_digamma1(update))) + ss
+            h = f(n_docs) * (K * K * f(trigamma(alpha_sum)) - K * f(trigamma(update)))
+            update = np.exp(np.log(update) - g / (h * update + g))
+            if abs(g) < ALPHA_CONVERGE:
+                break
+            if count > ALPHA_MAX_ITER:
+                break
+    return float(update)
